@@ -1,0 +1,23 @@
+"""efficient-visual-document-retrieval_b200 -- B200-native late-interaction (MaxSim) scoring.
+
+Drop-in for ONE hot path of kimjy-st/Efficient-Visual-Document-Retrieval: the ColPali-style MaxSim
+scorer (evaluator/retrieval.py:166-213), its backward, and the top-k / nDCG@k tail of evaluation.
+Host code is PyTorch (device memory, streams, torch.distributed) calling libevdr.so -- hand-written
+sm_100a CUDA behind the C ABI of include/evdr.h.  No Triton, no multi-backend dispatch, no CPU
+fallback: compute calls raise when the library or a B200 is missing.
+
+The directory name is not a Python identifier; import it with
+``importlib.import_module("efficient-visual-document-retrieval_b200")`` or through the alias
+package ``evdr_b200`` at the repository root.
+"""
+from . import _lib
+from . import corpus, normalize, retrieval, sharded, synth, topk
+from .corpus import PackedPages, pack_queries
+from .normalize import l2_normalize, l2_normalize_masked
+from .retrieval import (BaseVisualRetrieverProcessor, CustomRetrievalEvaluator, maxsim_exact,
+                        score_multi_vector_masked)
+from .sharded import ShardedSearch, init_nccl_comm, partition_pages
+from .topk import retrieval_metrics, topk as top_k, topk_merge
+
+__version__ = "0.1.0"
+SUBMODULES = ("_lib", "corpus", "normalize", "retrieval", "sharded", "synth", "topk")

@@ -1,0 +1,137 @@
+"""Packed page corpus: the HBM layout of the tensor-core MaxSim path.
+
+A corpus is a flat bf16 token stream ``tokens[n_tokens, 128]`` in which page ``c`` owns the
+16-token chunks ``chunk_off[c] .. chunk_off[c+1]``.  Masked / padded slots inside a page hold a
+duplicate of one of the page's valid tokens, so the scorer needs no mask at all; a page without
+valid tokens is all-zero tokens and scores exactly 0 like evaluator/retrieval.py:192,204.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import CHUNK, TC_DIM, TC_LQ
+
+
+def _mask_u8(mask: torch.Tensor) -> torch.Tensor:
+    """Masks of any dtype -> contiguous uint8, non-zero = valid (reference `.bool()`, :179-180)."""
+    if mask.dtype == torch.bool:
+        m = mask.contiguous().view(torch.uint8)
+    elif mask.dtype == torch.uint8:
+        m = (mask != 0).contiguous().view(torch.uint8)
+    else:
+        m = (mask != 0).contiguous().view(torch.uint8)
+    return m
+
+
+def _float_operand(t: torch.Tensor) -> torch.Tensor:
+    """fp32 / bf16 are consumed natively; other float dtypes are up-cast like the reference (:176-177)."""
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def pack_queries(Q: torch.Tensor, qmask: torch.Tensor):
+    """(nq, lq<=32, 128) -> bf16 (nq, 32, 128) with masked slots zeroed, uint8 (nq, 32)."""
+    _lib.require_cuda(Q, "Q")
+    nq, lq, d = Q.shape
+    Qc = _float_operand(Q)
+    qm = _mask_u8(qmask)
+    dev = Q.device
+    Qb = torch.empty((nq, TC_LQ, TC_DIM), dtype=torch.bfloat16, device=dev)
+    qm32 = torch.empty((nq, TC_LQ), dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.evdr_pack_queries(_lib.handle(dev), Qc.data_ptr(), _lib.dtype_code(Qc), qm.data_ptr(),
+                                     nq, lq, d, Qb.data_ptr(), qm32.data_ptr(), _lib.stream_ptr(dev)),
+               "evdr_pack_queries")
+    return Qb, qm32
+
+
+class PackedPages:
+    """Device-resident packed corpus shard."""
+
+    def __init__(self, tokens: torch.Tensor, chunk_off: torch.Tensor, n_pages: int, total_chunks: int,
+                 page_offset: int = 0):
+        self.tokens = tokens            # bf16 [n_tokens, 128]
+        self.chunk_off = chunk_off      # int32 [n_pages + 1]
+        self.n_pages = int(n_pages)
+        self.total_chunks = int(total_chunks)
+        self.page_offset = int(page_offset)   # global id of local page 0 (sharded corpora)
+        self.device = tokens.device
+
+    # ------------------------------------------------------------------ builders
+    @staticmethod
+    def from_padded(P: torch.Tensor, pmask: torch.Tensor, *, normalize: bool = False,
+                    varlen: bool = False, page_offset: int = 0) -> "PackedPages":
+        """Pack the reference's padded layout: P (np, lp, 128) fp32|bf16, pmask (np, lp) any dtype.
+
+        varlen=False sizes every page at ceil(lp/16) chunks (no host sync; right for the per-step
+        student tensor).  varlen=True trims each page after its last valid token (one device->host
+        read of the total; right for a corpus that is packed once).
+        normalize=True fuses l2_normalize(P * pmask[..., None]) (mainv2_iter_listwise.py:280).
+        """
+        _lib.require_cuda(P, "P")
+        npg, lp, d = P.shape
+        if d != TC_DIM:
+            raise NotImplementedError(f"tensor-core path needs d=128, got {d}")
+        Pc = _float_operand(P)
+        pm = _mask_u8(pmask)
+        dev = P.device
+        lib = _lib.load()
+        h = _lib.handle(dev)
+        st = _lib.stream_ptr(dev)
+        chunk_off = torch.empty(npg + 1, dtype=torch.int32, device=dev)
+        _lib.check(lib.evdr_pack_plan(h, pm.data_ptr(), npg, lp, 1 if varlen else 0, chunk_off.data_ptr(), st),
+                   "evdr_pack_plan")
+        if varlen:
+            total = int(chunk_off[-1].item())
+        else:
+            total = npg * ((lp + CHUNK - 1) // CHUNK)
+        tokens = torch.empty((total * CHUNK, TC_DIM), dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.evdr_pack_pages(h, Pc.data_ptr(), _lib.dtype_code(Pc), pm.data_ptr(),
+                                       chunk_off.data_ptr(), npg, lp, d, 1 if normalize else 0,
+                                       tokens.data_ptr(), st), "evdr_pack_pages")
+        return PackedPages(tokens, chunk_off, npg, total, page_offset)
+
+    @staticmethod
+    def from_uniform_tokens(tokens: torch.Tensor, page_offset: int = 0) -> "PackedPages":
+        """Zero-copy view of an all-valid bf16 corpus (np, L, 128) with L % 16 == 0."""
+        _lib.require_cuda(tokens, "tokens")
+        npg, L, d = tokens.shape
+        if tokens.dtype != torch.bfloat16 or d != TC_DIM or L % CHUNK != 0 or not tokens.is_contiguous():
+            raise ValueError("from_uniform_tokens needs contiguous bf16 (np, L%16==0, 128)")
+        cpp = L // CHUNK
+        chunk_off = torch.arange(0, (npg + 1) * cpp, cpp, dtype=torch.int32, device=tokens.device)
+        return PackedPages(tokens.view(npg * L, d), chunk_off, npg, npg * cpp, page_offset)
+
+    # ------------------------------------------------------------------ scoring
+    def score_packed(self, Qb: torch.Tensor, qm32: torch.Tensor, out: torch.Tensor | None = None,
+                     pages_per_item: int = 0) -> torch.Tensor:
+        """Tensor-core MaxSim of packed queries against this shard -> fp32 (nq, n_pages)."""
+        nq = Qb.shape[0]
+        dev = self.device
+        if out is None:
+            out = torch.empty((nq, self.n_pages), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        _lib.check(lib.evdr_maxsim_packed_fwd(
+            _lib.handle(dev), Qb.data_ptr(), qm32.data_ptr(), nq, self.tokens.data_ptr(),
+            self.tokens.shape[0], self.chunk_off.data_ptr(), self.n_pages, self.total_chunks,
+            pages_per_item, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)),
+            "evdr_maxsim_packed_fwd")
+        return out
+
+    def score(self, Q: torch.Tensor, qmask: torch.Tensor) -> torch.Tensor:
+        Qb, qm32 = pack_queries(Q, qmask)
+        return self.score_packed(Qb, qm32)
+
+    def search(self, Q: torch.Tensor, qmask: torch.Tensor, k: int = 10):
+        """Top-k pages per query: (scores (nq,k) fp32, ids (nq,k) int64 global page ids)."""
+        from .topk import topk
+        scores = self.score(Q, qmask)
+        return topk(scores, k, id_offset=self.page_offset)
+
+    @property
+    def nbytes(self) -> int:
+        return self.tokens.numel() * 2 + self.chunk_off.numel() * 4

@@ -1,0 +1,110 @@
+// common.cuh -- shared host/device helpers for libevdr.so (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/evdr.h"
+
+#define EVDR_VERSION_INT 100  // 0.1.0
+
+// ---------------------------------------------------------------------------
+// error plumbing: thread-local message + status code, no exceptions
+// ---------------------------------------------------------------------------
+namespace evdr {
+
+char* tls_error_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define EVDR_CHECK_ARG(cond, ...)                                        \
+  do {                                                                   \
+    if (!(cond)) return ::evdr::set_error(EVDR_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define EVDR_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess)                                                          \
+      return ::evdr::set_error(EVDR_ERR_CUDA, "%s failed: %s (%s:%d)", #call,        \
+                               cudaGetErrorString(e__), __FILE__, __LINE__);         \
+  } while (0)
+
+#define EVDR_LAUNCH_CHECK(name)                                                      \
+  do {                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess)                                                          \
+      return ::evdr::set_error(EVDR_ERR_CUDA, "launch of %s failed: %s", name,       \
+                               cudaGetErrorString(e__));                             \
+  } while (0)
+
+// NCCL function table, resolved with dlsym at evdr_comm_init (sharded.cu)
+struct NcclApi;
+
+}  // namespace evdr
+
+typedef CUresult (*evdr_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct evdr_handle {
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  size_t smem_optin;
+  evdr_encode_tiled_fn encode_tiled;
+  // multi-GPU
+  void* nccl_comm;  // ncclComm_t
+  int rank, world;
+};
+
+#define EVDR_REQUIRE_HANDLE(h)                                                        \
+  do {                                                                                \
+    if ((h) == nullptr) return ::evdr::set_error(EVDR_ERR_INVALID, "null handle");    \
+    cudaError_t e__ = cudaSetDevice((h)->device);                                     \
+    if (e__ != cudaSuccess)                                                           \
+      return ::evdr::set_error(EVDR_ERR_CUDA, "cudaSetDevice(%d): %s", (h)->device,   \
+                               cudaGetErrorString(e__));                              \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+namespace evdr {
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// load 4 consecutive elements as float4 (pointer must be aligned to 4 elements)
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 raw = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace evdr

@@ -1,0 +1,68 @@
+// evdr_core.cu -- handle, error string, version.  No compute here.
+#include "common.cuh"
+
+namespace evdr {
+
+char* tls_error_buf() {
+  static thread_local char buf[1024] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tls_error_buf(), 1024, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace evdr
+
+extern "C" {
+
+int evdr_version(void) { return EVDR_VERSION_INT; }
+
+const char* evdr_last_error(void) { return evdr::tls_error_buf(); }
+
+int evdr_create(int device, evdr_handle** out) {
+  EVDR_CHECK_ARG(out != nullptr, "evdr_create: out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return evdr::set_error(EVDR_ERR_CUDA,
+                           "no CUDA device visible (%s); libevdr has no CPU fallback",
+                           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  EVDR_CHECK_ARG(device >= 0 && device < ndev, "evdr_create: device %d out of range [0,%d)", device, ndev);
+  EVDR_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  EVDR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return evdr::set_error(EVDR_ERR_CUDA,
+                           "device %d is sm_%d%d; libevdr is built for sm_100a (B200) only",
+                           device, prop.major, prop.minor);
+  evdr_handle* h = new evdr_handle();
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->world = 1;
+  h->rank = 0;
+  // cuTensorMapEncodeTiled through the runtime, so the library needs no link-time libcuda.
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    delete h;
+    return evdr::set_error(EVDR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  }
+  h->encode_tiled = reinterpret_cast<evdr_encode_tiled_fn>(fn);
+  *out = h;
+  return EVDR_OK;
+}
+
+int evdr_sm_count(const evdr_handle* h) { return h ? h->sm_count : 0; }
+
+}  // extern "C"

@@ -1,0 +1,355 @@
+// maxsim_simt.cu -- general exact MaxSim (fp32 FMA) forward with argmax, and the
+// deterministic backward.  This is the path for shapes the tensor-core kernel does
+// not cover (d != 128, lq > 32), for the fp32-exact mode and for training (argmax).
+//
+// Reference semantics: evaluator/retrieval.py:166-213 (forward), SURVEY 8a A5 (backward).
+#include "common.cuh"
+
+namespace evdr {
+
+constexpr int BM = 64;   // query-token rows per CTA
+constexpr int BN = 64;   // page tokens per inner tile
+constexpr int BK = 32;   // reduction chunk
+constexpr float kNegFill = -1e4f;  // evaluator/retrieval.py:185
+
+// rowmax[c*R + r], argmax[c*R + r] for r = q*lq + n  (page-major workspace layout)
+template <typename TQ, typename TP>
+__global__ void __launch_bounds__(256)
+rowmax_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P,
+              const uint8_t* __restrict__ pmask, int R, int lp, int d,
+              float* __restrict__ rowmax, int32_t* __restrict__ argmax) {
+  __shared__ float As[BK][BM + 1];
+  __shared__ float Bs[BK][BN + 1];
+  __shared__ uint8_t Ms[BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;        // column group
+  const int ty = tid >> 4;        // row group
+  const int row0 = blockIdx.x * BM;
+  const int c = blockIdx.y;
+  const TP* Pc = P + (size_t)c * lp * d;
+  const uint8_t* mc = pmask + (size_t)c * lp;
+
+  float best[4];
+  int bidx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { best[i] = -INFINITY; bidx[i] = 0; }
+
+  for (int m0 = 0; m0 < lp; m0 += BN) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    if (tid < BN) Ms[tid] = (m0 + tid < lp) ? mc[m0 + tid] : (uint8_t)0;
+
+    for (int k0 = 0; k0 < d; k0 += BK) {
+#pragma unroll
+      for (int i = 0; i < (BM * BK) / 256; ++i) {
+        int idx = tid + i * 256;
+        int r = idx / BK, k = idx % BK;
+        float va = 0.f, vb = 0.f;
+        if (k0 + k < d) {
+          if (row0 + r < R) va = to_f32(Q[(size_t)(row0 + r) * d + k0 + k]);
+          if (m0 + r < lp) vb = to_f32(Pc[(size_t)(m0 + r) * d + k0 + k]);
+        }
+        As[k][r] = va;
+        Bs[k][r] = vb;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+    // masked running max; page tokens visited in ascending order, strict '>' keeps the first index
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int m = m0 + tx * 4 + j;
+      if (m < lp) {
+        bool valid = Ms[tx * 4 + j] != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = valid ? acc[i][j] : kNegFill;
+          if (v > best[i]) { best[i] = v; bidx[i] = m; }
+        }
+      }
+    }
+    __syncthreads();  // Ms reuse
+  }
+  // reduce across the 16 column groups (contiguous half-warp lanes)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = best[i];
+    int ix = bidx[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+      if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+    }
+    int r = row0 + ty * 4 + i;
+    if (tx == 0 && r < R) {
+      rowmax[(size_t)c * R + r] = v;
+      if (argmax) argmax[(size_t)c * R + r] = ix;
+    }
+  }
+}
+
+// out[q, c] = has[c] * sum_n qmask[q,n] * rowmax[c*R + q*lq + n]; one warp per page.
+__global__ void __launch_bounds__(256)
+rowsum_kernel(const float* __restrict__ rowmax, const uint8_t* __restrict__ qmask,
+              const uint8_t* __restrict__ pmask, int nq, int np, int lq, int lp,
+              float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= np) return;
+  int any = 0;
+  for (int m = lane; m < lp; m += 32) any |= pmask[(size_t)c * lp + m];
+  any = __any_sync(0xffffffffu, any != 0);
+  const float has = any ? 1.f : 0.f;
+  const int R = nq * lq;
+  const float* rm = rowmax + (size_t)c * R;
+  for (int q = 0; q < nq; ++q) {
+    float s = 0.f;
+    for (int n = lane; n < lq; n += 32) {
+      float w = qmask[(size_t)q * lq + n] ? 1.f : 0.f;
+      s += (rm[q * lq + n] * has) * w;
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[(size_t)q * np + c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backward dP: one CTA per page.  Stable bucket of query-token rows by their
+// argmax page token (ascending row order inside each bucket), then each warp sums
+// its tokens' rows in that order: deterministic, no floating-point atomics.
+// dynamic smem: cnt[lp] + off[lp+1] + list[R] ints.
+// ---------------------------------------------------------------------------
+template <typename TQ>
+__global__ void __launch_bounds__(256)
+bwd_dp_kernel(const float* __restrict__ gout, const TQ* __restrict__ Q,
+              const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ pmask,
+              const int32_t* __restrict__ argmax, int nq, int np, int lq, int lp, int d,
+              float* __restrict__ dP) {
+  extern __shared__ int smem_i[];
+  int* cnt = smem_i;            // lp
+  int* off = cnt + lp;          // lp + 1
+  int* list = off + lp + 1;     // R
+  __shared__ int s_has;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x;
+  const int R = nq * lq;
+  const int32_t* am = argmax + (size_t)c * R;
+
+  if (tid == 0) s_has = 0;
+  for (int m = tid; m < lp; m += blockDim.x) cnt[m] = 0;
+  __syncthreads();
+  int any = 0;
+  for (int m = tid; m < lp; m += blockDim.x) any |= pmask[(size_t)c * lp + m];
+  if (any) s_has = 1;
+  __syncthreads();
+  float* dPc = dP + (size_t)c * lp * d;
+  if (!s_has) {  // empty page: zero gradient (evaluator/retrieval.py:204)
+    for (int i = tid; i < lp * d; i += blockDim.x) dPc[i] = 0.f;
+    return;
+  }
+  for (int r = tid; r < R; r += blockDim.x)
+    if (qmask[r]) atomicAdd(&cnt[am[r]], 1);
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan over lp counters
+    int carry = 0;
+    for (int m0 = 0; m0 < lp; m0 += 32) {
+      int m = m0 + lane;
+      int v = (m < lp) ? cnt[m] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (m < lp) off[m] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) off[lp] = carry;
+    __syncwarp();
+    // stable fill: rows in ascending order, 32 at a time
+    for (int m = lane; m < lp; m += 32) cnt[m] = 0;
+    __syncwarp();
+    for (int r0 = 0; r0 < R; r0 += 32) {
+      int r = r0 + lane;
+      bool act = (r < R) && qmask[r];
+      int m = act ? am[r] : -1 - lane;  // inactive lanes get unique keys
+      unsigned peers = __match_any_sync(0xffffffffu, m);
+      if (act) {
+        int rank = __popc(peers & ((1u << lane) - 1u));
+        int base = cnt[m];
+        list[off[m] + base + rank] = r;
+      }
+      __syncwarp();
+      if (act && (__ffs(peers) - 1) == lane) cnt[m] += __popc(peers);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const int nwarps = blockDim.x >> 5;
+  for (int m = warp; m < lp; m += nwarps) {
+    const int b = off[m], e = off[m + 1];
+    for (int d0 = lane * 4; d0 < d; d0 += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = b; i < e; ++i) {
+        int r = list[i];
+        float w = gout[(size_t)(r / lq) * np + c];
+        float4 qv = load4(Q + (size_t)r * d + d0);
+        acc.x = fmaf(w, qv.x, acc.x);
+        acc.y = fmaf(w, qv.y, acc.y);
+        acc.z = fmaf(w, qv.z, acc.z);
+        acc.w = fmaf(w, qv.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(dPc + (size_t)m * d + d0) = acc;
+    }
+  }
+}
+
+// backward dQ: one warp per query-token row, pages in ascending order.
+template <typename TP>
+__global__ void __launch_bounds__(256)
+bwd_dq_kernel(const float* __restrict__ gout, const TP* __restrict__ P,
+              const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ has_page,
+              const int32_t* __restrict__ argmax, int nq, int np, int lq, int lp, int d,
+              float* __restrict__ dQ) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int R = nq * lq;
+  if (r >= R) return;
+  const int q = r / lq;
+  const bool act = qmask[r] != 0;
+  for (int d0 = lane * 4; d0 < d; d0 += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+      for (int c = 0; c < np; ++c) {
+        if (!has_page[c]) continue;
+        float w = gout[(size_t)q * np + c];
+        int m = argmax[(size_t)c * R + r];
+        float4 pv = load4(P + ((size_t)c * lp + m) * d + d0);
+        acc.x = fmaf(w, pv.x, acc.x);
+        acc.y = fmaf(w, pv.y, acc.y);
+        acc.z = fmaf(w, pv.z, acc.z);
+        acc.w = fmaf(w, pv.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(dQ + (size_t)r * d + d0) = acc;
+  }
+}
+
+__global__ void has_page_kernel(const uint8_t* __restrict__ pmask, int np, int lp,
+                                uint8_t* __restrict__ has) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= np) return;
+  int any = 0;
+  for (int m = lane; m < lp; m += 32) any |= pmask[(size_t)c * lp + m];
+  any = __any_sync(0xffffffffu, any != 0);
+  if (lane == 0) has[c] = any ? 1 : 0;
+}
+
+template <typename TQ, typename TP>
+static int launch_fwd(const void* Q, const void* P, const uint8_t* pmask, int R, int np, int lp,
+                      int d, float* rowmax, int32_t* argmax, cudaStream_t st) {
+  dim3 grid((R + BM - 1) / BM, np);
+  rowmax_kernel<TQ, TP><<<grid, 256, 0, st>>>(static_cast<const TQ*>(Q), static_cast<const TP*>(P),
+                                              pmask, R, lp, d, rowmax, argmax);
+  EVDR_LAUNCH_CHECK("rowmax_kernel");
+  return EVDR_OK;
+}
+
+}  // namespace evdr
+
+using namespace evdr;
+
+extern "C" {
+
+int evdr_maxsim_fwd(evdr_handle* h, const void* Q, int q_dtype, const void* P, int p_dtype,
+                    const uint8_t* qmask, const uint8_t* pmask, int nq, int np, int lq, int lp,
+                    int d, float* rowmax_ws, int32_t* argmax, float* out, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(Q && P && qmask && pmask && rowmax_ws && out, "evdr_maxsim_fwd: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && lq >= 1 && lp >= 1 && d >= 4 && d % 4 == 0,
+                 "evdr_maxsim_fwd: bad shape nq=%d np=%d lq=%d lp=%d d=%d", nq, np, lq, lp, d);
+  EVDR_CHECK_ARG((q_dtype == EVDR_F32 || q_dtype == EVDR_BF16) && (p_dtype == EVDR_F32 || p_dtype == EVDR_BF16),
+                 "evdr_maxsim_fwd: dtype must be EVDR_F32 or EVDR_BF16");
+  EVDR_CHECK_ARG(np <= 65535, "evdr_maxsim_fwd: np=%d > 65535 pages per call (chunk the page axis)", np);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int R = nq * lq;
+  int rc;
+  if (q_dtype == EVDR_F32 && p_dtype == EVDR_F32)
+    rc = launch_fwd<float, float>(Q, P, pmask, R, np, lp, d, rowmax_ws, argmax, st);
+  else if (q_dtype == EVDR_F32)
+    rc = launch_fwd<float, __nv_bfloat16>(Q, P, pmask, R, np, lp, d, rowmax_ws, argmax, st);
+  else if (p_dtype == EVDR_F32)
+    rc = launch_fwd<__nv_bfloat16, float>(Q, P, pmask, R, np, lp, d, rowmax_ws, argmax, st);
+  else
+    rc = launch_fwd<__nv_bfloat16, __nv_bfloat16>(Q, P, pmask, R, np, lp, d, rowmax_ws, argmax, st);
+  if (rc != EVDR_OK) return rc;
+  rowsum_kernel<<<(np + 7) / 8, 256, 0, st>>>(rowmax_ws, qmask, pmask, nq, np, lq, lp, out);
+  EVDR_LAUNCH_CHECK("rowsum_kernel");
+  return EVDR_OK;
+}
+
+int evdr_maxsim_bwd(evdr_handle* h, const float* gout, const void* Q, int q_dtype, const void* P,
+                    int p_dtype, const uint8_t* qmask, const uint8_t* pmask, const int32_t* argmax,
+                    int nq, int np, int lq, int lp, int d, float* dP, float* dQ, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(gout && Q && P && qmask && pmask && argmax, "evdr_maxsim_bwd: null pointer");
+  EVDR_CHECK_ARG(dP || dQ, "evdr_maxsim_bwd: both dP and dQ are null");
+  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && lq >= 1 && lp >= 1 && d >= 4 && d % 4 == 0,
+                 "evdr_maxsim_bwd: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int R = nq * lq;
+  if (dP) {
+    size_t smem = sizeof(int) * ((size_t)lp + lp + 1 + R);
+    if (smem > h->smem_optin)
+      return set_error(EVDR_ERR_UNSUPPORTED,
+                       "evdr_maxsim_bwd: nq*lq=%d rows + lp=%d need %zu B of shared memory (> %zu)",
+                       R, lp, smem, h->smem_optin);
+    if (q_dtype == EVDR_F32) {
+      EVDR_CUDA(cudaFuncSetAttribute(bwd_dp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bwd_dp_kernel<float><<<np, 256, smem, st>>>(gout, static_cast<const float*>(Q), qmask, pmask,
+                                                  argmax, nq, np, lq, lp, d, dP);
+    } else {
+      EVDR_CUDA(cudaFuncSetAttribute(bwd_dp_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bwd_dp_kernel<__nv_bfloat16><<<np, 256, smem, st>>>(gout, static_cast<const __nv_bfloat16*>(Q),
+                                                          qmask, pmask, argmax, nq, np, lq, lp, d, dP);
+    }
+    EVDR_LAUNCH_CHECK("bwd_dp_kernel");
+  }
+  if (dQ) {
+    uint8_t* has = nullptr;
+    EVDR_CUDA(cudaMallocAsync(&has, np, st));
+    has_page_kernel<<<(np + 7) / 8, 256, 0, st>>>(pmask, np, lp, has);
+    EVDR_LAUNCH_CHECK("has_page_kernel");
+    if (p_dtype == EVDR_F32)
+      bwd_dq_kernel<float><<<(R + 7) / 8, 256, 0, st>>>(gout, static_cast<const float*>(P), qmask, has,
+                                                        argmax, nq, np, lq, lp, d, dQ);
+    else
+      bwd_dq_kernel<__nv_bfloat16><<<(R + 7) / 8, 256, 0, st>>>(
+          gout, static_cast<const __nv_bfloat16*>(P), qmask, has, argmax, nq, np, lq, lp, d, dQ);
+    EVDR_LAUNCH_CHECK("bwd_dq_kernel");
+    EVDR_CUDA(cudaFreeAsync(has, st));
+  }
+  return EVDR_OK;
+}
+
+}  // extern "C"

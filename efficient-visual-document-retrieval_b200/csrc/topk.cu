@@ -1,0 +1,298 @@
+// topk.cu -- evaluation tail on device: warp-level top-k selection, candidate
+// merge, and trec_eval-style measures.
+//
+// Replaces the reference's Nq*Np `.item()` dict build (mainv2_iter_listwise.py:312-318)
+// plus mteb/pytrec_eval behind evaluator/retrieval.py:239-246.
+//
+// Ordering key everywhere: score descending, then tie key ascending, then position
+// ascending (only to separate padding sentinels).  The tie key is tie_rank[col] when
+// given (host passes the rank of the docid string in descending order = trec_eval's
+// rule) else the column index / candidate id.
+#include "common.cuh"
+
+namespace evdr {
+
+constexpr int TOPK_MAX = 128;
+constexpr int TOPK_WARPS = 8;
+
+struct Cand {
+  float s;
+  int tie;
+  long long id;
+};
+
+__device__ __forceinline__ bool better(float s, long long t, float os, long long ot) {
+  return (s > os) || (s == os && t < ot);
+}
+
+// Per-warp sorted list in shared memory (best first), k entries.
+struct WarpList {
+  float* s;
+  long long* tie;
+  long long* id;
+};
+
+// Insert candidate (cs, ct, cid) held by all lanes (already known to beat the worst).
+__device__ __forceinline__ void warp_insert(const WarpList& L, int k, int lane, float cs,
+                                            long long ct, long long cid) {
+  // position = number of entries better than the candidate
+  int pos = 0;
+  for (int j0 = 0; j0 < k; j0 += 32) {
+    int j = j0 + lane;
+    bool b = (j < k) && better(L.s[j], L.tie[j], cs, ct);
+    pos += __popc(__ballot_sync(0xffffffffu, b));
+  }
+  // shift [pos, k-2] down by one, from the tail, 32 entries at a time
+  for (int hi = k - 1; hi > pos; hi -= 32) {
+    int j = hi - lane;  // destination index
+    float ts = 0.f; long long tt = 0, ti = 0;
+    bool mv = (j > pos);
+    if (mv) { ts = L.s[j - 1]; tt = L.tie[j - 1]; ti = L.id[j - 1]; }
+    __syncwarp();
+    if (mv) { L.s[j] = ts; L.tie[j] = tt; L.id[j] = ti; }
+    __syncwarp();
+  }
+  if (lane == 0) { L.s[pos] = cs; L.tie[pos] = ct; L.id[pos] = cid; }
+  __syncwarp();
+}
+
+// grid (nsplit, nq).  Source is either implicit columns of a score row
+// (cand_ids == nullptr: id = col + id_offset, tie = tie_rank ? tie_rank[col] : col)
+// or explicit candidates (tie = cand_tie ? cand_tie[i] : cand_ids[i]).
+__global__ void __launch_bounds__(TOPK_WARPS * 32)
+topk_select_kernel(const float* __restrict__ scores, long long ld, int n,
+                   const int32_t* __restrict__ tie_rank, long long id_offset,
+                   const long long* __restrict__ cand_ids, const long long* __restrict__ cand_tie,
+                   int k, float* __restrict__ out_s, long long* __restrict__ out_tie,
+                   long long* __restrict__ out_id) {
+  extern __shared__ unsigned char smem_raw[];
+  // layout: per warp k floats, k tie, k id
+  float* ws = reinterpret_cast<float*>(smem_raw);
+  long long* wt = reinterpret_cast<long long*>(smem_raw + sizeof(float) * TOPK_WARPS * TOPK_MAX);
+  long long* wi = wt + TOPK_WARPS * TOPK_MAX;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.y;
+  const int nsplit = gridDim.x;
+  const int seg = (n + nsplit - 1) / nsplit;
+  const int beg = blockIdx.x * seg;
+  const int end = min(n, beg + seg);
+  const float* row = scores + (size_t)q * ld;
+  const long long* idrow = cand_ids ? cand_ids + (size_t)q * ld : nullptr;
+  const long long* tierow = cand_tie ? cand_tie + (size_t)q * ld : nullptr;
+
+  WarpList L{ws + warp * TOPK_MAX, wt + warp * TOPK_MAX, wi + warp * TOPK_MAX};
+  for (int j = lane; j < k; j += 32) {
+    L.s[j] = -INFINITY;
+    L.tie[j] = 0x7fffffffffffffffLL;
+    L.id[j] = -1;
+  }
+  __syncwarp();
+  float thr_s = -INFINITY;
+  long long thr_t = 0x7fffffffffffffffLL;
+
+  for (int base = beg + warp * 32; base < end; base += TOPK_WARPS * 32) {
+    int i = base + lane;
+    float s = -INFINITY;
+    long long t = 0x7fffffffffffffffLL, id = -1;
+    bool ok = false;
+    if (i < end) {
+      s = row[i];
+      if (idrow) {
+        id = idrow[i];
+        t = tierow ? tierow[i] : id;
+        ok = id >= 0;
+      } else {
+        id = (long long)i + id_offset;
+        t = tie_rank ? (long long)tie_rank[i] : (long long)i;
+        ok = true;
+      }
+      ok = ok && better(s, t, thr_s, thr_t);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    while (m) {
+      int src = __ffs(m) - 1;
+      m &= m - 1;
+      float cs = __shfl_sync(0xffffffffu, s, src);
+      long long ct = __shfl_sync(0xffffffffu, t, src);
+      long long cid = __shfl_sync(0xffffffffu, id, src);
+      if (better(cs, ct, thr_s, thr_t)) {  // threshold may have moved
+        warp_insert(L, k, lane, cs, ct, cid);
+        thr_s = L.s[k - 1];
+        thr_t = L.tie[k - 1];
+      }
+    }
+  }
+  __syncthreads();
+  // block merge: rank every entry of the 8 lists among all of them
+  const int total = TOPK_WARPS * k;
+  float* os = out_s + ((size_t)q * nsplit + blockIdx.x) * k;
+  long long* ot = out_tie ? out_tie + ((size_t)q * nsplit + blockIdx.x) * k : nullptr;
+  long long* oi = out_id + ((size_t)q * nsplit + blockIdx.x) * k;
+  for (int e = tid; e < total; e += blockDim.x) {
+    int w = e / k, j = e % k;
+    float s = ws[w * TOPK_MAX + j];
+    long long t = wt[w * TOPK_MAX + j];
+    int rank = 0;
+    for (int f = 0; f < total; ++f) {
+      int fw = f / k, fj = f % k;
+      float fs = ws[fw * TOPK_MAX + fj];
+      long long ft = wt[fw * TOPK_MAX + fj];
+      if (better(fs, ft, s, t) || (fs == s && ft == t && f < e)) ++rank;
+    }
+    if (rank < k) {
+      os[rank] = s;
+      if (ot) ot[rank] = t;
+      oi[rank] = wi[w * TOPK_MAX + j];
+    }
+  }
+}
+
+// trec_eval-style per-query measures; one thread per query, double accumulators.
+// out[m][j][q], m: 0 ndcg, 1 map, 2 recall, 3 precision, 4 mrr
+__global__ void __launch_bounds__(128)
+metrics_kernel(const long long* __restrict__ top_ids, int kmax, int nq,
+               const int32_t* __restrict__ qrel_off, const long long* __restrict__ qrel_ids,
+               const int32_t* __restrict__ qrel_rels, const int32_t* __restrict__ k_values, int nk,
+               double* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int b = qrel_off[q], e = qrel_off[q + 1];
+  int n_rel = 0;
+  for (int i = b; i < e; ++i) n_rel += qrel_rels[i] > 0;
+  const long long* ids = top_ids + (size_t)q * kmax;
+  for (int j = 0; j < nk; ++j) {
+    const int k = k_values[j];
+    const int kk = min(k, kmax);
+    double dcg = 0.0, ap = 0.0, rr = 0.0;
+    int hits = 0;
+    for (int i = 0; i < kk; ++i) {
+      long long id = ids[i];
+      int rel = 0;
+      if (id >= 0)
+        for (int t = b; t < e; ++t)
+          if (qrel_ids[t] == id) { rel = qrel_rels[t]; break; }
+      if (rel > 0) {
+        dcg += (double)rel / log2((double)i + 2.0);
+        ++hits;
+        ap += (double)hits / (double)(i + 1);
+        if (rr == 0.0) rr = 1.0 / (double)(i + 1);
+      }
+    }
+    // ideal DCG: positive rels in descending order, cut at k (selection without storage)
+    double idcg = 0.0;
+    {
+      int last_rel = 0x7fffffff;  // rels emitted so far are >= last_rel
+      int emitted = 0;
+      while (emitted < k && emitted < n_rel) {
+        // next largest value strictly below last_rel, and how many have it
+        int best = 0, cnt = 0;
+        for (int t = b; t < e; ++t) {
+          int r = qrel_rels[t];
+          if (r > 0 && r < last_rel) {
+            if (r > best) { best = r; cnt = 1; }
+            else if (r == best) ++cnt;
+          }
+        }
+        if (best == 0) break;
+        for (int c = 0; c < cnt && emitted < k; ++c, ++emitted)
+          idcg += (double)best / log2((double)emitted + 2.0);
+        last_rel = best;
+      }
+    }
+    const size_t o = (size_t)j * nq + q;
+    const size_t plane = (size_t)nk * nq;
+    out[0 * plane + o] = idcg > 0.0 ? dcg / idcg : 0.0;
+    out[1 * plane + o] = n_rel > 0 ? ap / (double)n_rel : 0.0;
+    out[2 * plane + o] = n_rel > 0 ? (double)hits / (double)n_rel : 0.0;
+    out[3 * plane + o] = (double)hits / (double)k;
+    out[4 * plane + o] = rr;
+  }
+}
+
+static int pick_nsplit(const evdr_handle* h, int nq, int n) {
+  int want = (2 * h->sm_count + nq - 1) / nq;          // fill the GPU twice over
+  int cap = (n + 4095) / 4096;                          // >= 4096 columns per CTA
+  int ns = want < cap ? want : cap;
+  return ns < 1 ? 1 : ns;
+}
+
+static size_t topk_smem() {
+  return (sizeof(float) + 2 * sizeof(long long)) * (size_t)TOPK_WARPS * TOPK_MAX;
+}
+
+// two-stage selection shared by evdr_topk / evdr_topk_merge
+static int run_topk(evdr_handle* h, const float* scores, long long ld, int nq, int n,
+                    const int32_t* tie_rank, long long id_offset, const long long* cand_ids,
+                    int k, float* top_s, long long* top_id, cudaStream_t st) {
+  const size_t smem = topk_smem();
+  EVDR_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nsplit = pick_nsplit(h, nq, n);
+  if (nsplit == 1) {
+    topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
+        scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, top_s, nullptr, top_id);
+    EVDR_LAUNCH_CHECK("topk_select_kernel");
+    return EVDR_OK;
+  }
+  const size_t per = (size_t)nq * nsplit * k;
+  unsigned char* ws = nullptr;
+  EVDR_CUDA(cudaMallocAsync(&ws, per * (sizeof(float) + 2 * sizeof(long long)), st));
+  long long* p_tie = reinterpret_cast<long long*>(ws);
+  long long* p_id = p_tie + per;
+  float* p_s = reinterpret_cast<float*>(p_id + per);
+  topk_select_kernel<<<dim3(nsplit, nq), TOPK_WARPS * 32, smem, st>>>(
+      scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, p_s, p_tie, p_id);
+  EVDR_LAUNCH_CHECK("topk_select_kernel(stage1)");
+  topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
+      p_s, (long long)nsplit * k, nsplit * k, nullptr, 0, p_id, p_tie, k, top_s, nullptr, top_id);
+  EVDR_LAUNCH_CHECK("topk_select_kernel(stage2)");
+  EVDR_CUDA(cudaFreeAsync(ws, st));
+  return EVDR_OK;
+}
+
+}  // namespace evdr
+
+using namespace evdr;
+
+extern "C" {
+
+int evdr_topk(evdr_handle* h, const float* scores, int64_t ld, int nq, int np, int k,
+              const int32_t* tie_rank, int64_t id_offset, float* top_scores, int64_t* top_ids,
+              void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(scores && top_scores && top_ids, "evdr_topk: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && ld >= np, "evdr_topk: bad shape nq=%d np=%d ld=%lld", nq, np, (long long)ld);
+  EVDR_CHECK_ARG(k >= 1 && k <= TOPK_MAX, "evdr_topk: k=%d outside [1,%d]", k, TOPK_MAX);
+  EVDR_CHECK_ARG(nq <= 65535, "evdr_topk: nq=%d > 65535 per call", nq);
+  return run_topk(h, scores, ld, nq, np, tie_rank, id_offset, nullptr, k, top_scores,
+                  reinterpret_cast<long long*>(top_ids), static_cast<cudaStream_t>(stream));
+}
+
+int evdr_topk_merge(evdr_handle* h, const float* cand_scores, const int64_t* cand_ids, int nq,
+                    int ncand, int k, float* top_scores, int64_t* top_ids, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(cand_scores && cand_ids && top_scores && top_ids, "evdr_topk_merge: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && ncand >= 1, "evdr_topk_merge: bad shape");
+  EVDR_CHECK_ARG(k >= 1 && k <= TOPK_MAX, "evdr_topk_merge: k=%d outside [1,%d]", k, TOPK_MAX);
+  EVDR_CHECK_ARG(nq <= 65535, "evdr_topk_merge: nq=%d > 65535 per call", nq);
+  return run_topk(h, cand_scores, ncand, nq, ncand, nullptr, 0,
+                  reinterpret_cast<const long long*>(cand_ids), k, top_scores,
+                  reinterpret_cast<long long*>(top_ids), static_cast<cudaStream_t>(stream));
+}
+
+int evdr_retrieval_metrics(evdr_handle* h, const int64_t* top_ids, int kmax, int nq,
+                           const int32_t* qrel_off, const int64_t* qrel_ids,
+                           const int32_t* qrel_rels, const int32_t* k_values, int nk, double* out,
+                           void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(top_ids && qrel_off && qrel_ids && qrel_rels && k_values && out,
+                 "evdr_retrieval_metrics: null pointer");
+  EVDR_CHECK_ARG(kmax >= 1 && nq >= 1 && nk >= 1, "evdr_retrieval_metrics: bad shape");
+  metrics_kernel<<<(nq + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(top_ids), kmax, nq, qrel_off,
+      reinterpret_cast<const long long*>(qrel_ids), qrel_rels, k_values, nk, out);
+  EVDR_LAUNCH_CHECK("metrics_kernel");
+  return EVDR_OK;
+}
+
+}  // extern "C"

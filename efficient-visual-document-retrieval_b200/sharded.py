@@ -1,0 +1,95 @@
+"""Multi-GPU retrieval: the page corpus is sharded by contiguous page range across the ranks of
+one box (one process per GPU), queries are replicated, every rank computes a local top-k and the
+candidates are merged after ONE all-gather.  There is no other data-path collective.
+
+Two exchange modes:
+* "nccl"  (default on CUDA): `evdr_sharded_topk` -- local top-k, ncclAllGather of nq*k (score, id)
+  pairs on the caller's stream and the merge kernel, all inside libevdr.so;
+* "torchdist": the same three steps with the all-gather done by torch.distributed on whatever
+  backend the process group has.  This is what the world_size-2 gloo tests exercise on CPU with the
+  oracle's top-k / merge injected in place of the CUDA kernels (host logic only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def partition_pages(n_pages: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous page ranges [start, end) per rank; the first n_pages % world ranks get one extra."""
+    base, rem = divmod(n_pages, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def init_nccl_comm(device: torch.device, group=None) -> None:
+    """Create libevdr's NCCL communicator for this rank: rank 0 makes the unique id, torch.distributed
+    (the plumbing) broadcasts it, every rank calls evdr_comm_init."""
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        _lib.check(lib.evdr_comm_unique_id(C.cast(buf, C.c_void_p)), "evdr_comm_unique_id")
+        uid = torch.tensor(list(buf), dtype=torch.uint8)
+    backend = dist.get_backend(group)
+    t = uid.to(device) if backend == "nccl" else uid
+    dist.broadcast(t, src=0, group=group)
+    raw = bytes(t.cpu().tolist())
+    buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+    _lib.check(lib.evdr_comm_init(_lib.handle(device), C.cast(buf, C.c_void_p), rank, world), "evdr_comm_init")
+
+
+class ShardedSearch:
+    """Global top-k over per-rank score blocks.
+
+    local_topk(scores, k, id_offset) -> (top_scores, top_ids) and merge(cand_scores, cand_ids, k) ->
+    (top_scores, top_ids) default to the CUDA kernels; tests inject CPU doubles.
+    """
+
+    def __init__(self, page_range: Tuple[int, int], *, mode: str = "nccl", group=None,
+                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None):
+        self.start, self.end = page_range
+        self.mode = mode
+        self.group = group
+        if local_topk is None or merge is None:
+            from .topk import topk as _topk, topk_merge as _merge
+            local_topk = local_topk or (lambda s, k, off: _topk(s, k, id_offset=off))
+            merge = merge or _merge
+        self._local_topk = local_topk
+        self._merge = merge
+
+    def topk(self, local_scores: torch.Tensor, k: int):
+        """local_scores (nq, n_local_pages) fp32 -> global (scores (nq,k), ids (nq,k)) on every rank."""
+        nq, n_local = local_scores.shape
+        assert n_local == self.end - self.start, "score block does not match this rank's page range"
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if self.mode == "nccl":
+            dev = local_scores.device
+            _lib.require_cuda(local_scores, "local_scores")
+            top_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            top_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            if local_scores.stride(1) != 1:
+                local_scores = local_scores.contiguous()
+            lib = _lib.load()
+            _lib.check(lib.evdr_sharded_topk(_lib.handle(dev), local_scores.data_ptr(), local_scores.stride(0),
+                                             nq, n_local, k, self.start, top_s.data_ptr(), top_i.data_ptr(),
+                                             _lib.stream_ptr(dev)), "evdr_sharded_topk")
+            return top_s, top_i
+        loc_s, loc_i = self._local_topk(local_scores, k, self.start)
+        if world == 1:
+            return loc_s, loc_i
+        gs = [torch.empty_like(loc_s) for _ in range(world)]
+        gi = [torch.empty_like(loc_i) for _ in range(world)]
+        dist.all_gather(gs, loc_s.contiguous(), group=self.group)
+        dist.all_gather(gi, loc_i.contiguous(), group=self.group)
+        return self._merge(torch.cat(gs, dim=1), torch.cat(gi, dim=1), k)

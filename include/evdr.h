@@ -1,0 +1,209 @@
+/* evdr.h -- C ABI of libevdr.so: B200-native late-interaction (MaxSim) scoring.
+ *
+ * Drop-in boundary for ONE path of kimjy-st/Efficient-Visual-Document-Retrieval:
+ * the ColPali-style MaxSim scorer, its backward, and the top-k / nDCG@k tail of
+ * evaluation.  The reference has no FFI of its own; its "operator API" is the
+ * Python signature `score_multi_vector_masked(Q, P, qmask, pmask, chunk_p)`
+ * (evaluator/retrieval.py:166-213) imported by name by all 21 main*.py scripts.
+ * The Python mirror of that signature (package `efficient-visual-document-
+ * retrieval_b200`, module `retrieval`) binds exactly the entry points below via
+ * ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - every pointer named `*_dev` / documented "device" is a CUDA device pointer
+ *    owned by the caller (a torch allocation); the library allocates nothing
+ *    persistent except the opaque handle;
+ *  - all launches go to the caller's stream (`stream` is a cudaStream_t passed as
+ *    void*; NULL = legacy default stream); no hidden synchronisation unless the
+ *    function says so;
+ *  - every function returns 0 on success, <0 on error (enum evdr_status) and
+ *    records a thread-local message retrievable with evdr_last_error();
+ *  - no C++ exceptions and no torch types cross this boundary;
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    EVDR_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef EVDR_H_
+#define EVDR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define EVDR_API
+#else
+#define EVDR_API __attribute__((visibility("default")))
+#endif
+
+typedef struct evdr_handle evdr_handle;
+
+enum evdr_status {
+  EVDR_OK = 0,
+  EVDR_ERR_INVALID = -1,     /* bad argument / shape */
+  EVDR_ERR_CUDA = -2,        /* CUDA runtime / driver error, or no sm_100 device */
+  EVDR_ERR_UNSUPPORTED = -3, /* shape outside what the kernel family covers */
+  EVDR_ERR_NCCL = -4,        /* NCCL not loadable or collective failed */
+  EVDR_ERR_STATE = -5        /* call order (e.g. sharded op before comm_init) */
+};
+
+enum evdr_dtype { EVDR_F32 = 0, EVDR_BF16 = 1 };
+
+/* Packed page stream granularity: every page occupies a whole number of
+ * EVDR_CHUNK-token slots in the bf16 token stream. */
+#define EVDR_CHUNK 16
+/* Tensor-core path operand geometry (ColPali): 128-d tokens, queries padded to
+ * 32 token slots (one warp of epilogue lanes per query). */
+#define EVDR_TC_DIM 128
+#define EVDR_TC_LQ 32
+
+EVDR_API int evdr_version(void);
+EVDR_API const char* evdr_last_error(void);
+
+/* Handle: per (thread, device); holds the device ordinal, SM count, the driver
+ * entry point used to encode TMA descriptors and, after evdr_comm_init, the NCCL
+ * communicator.  Not thread-safe. */
+EVDR_API int evdr_create(int device, evdr_handle** out);
+EVDR_API int evdr_destroy(evdr_handle* h);
+EVDR_API int evdr_sm_count(const evdr_handle* h);
+
+/* ------------------------------------------------------------------------
+ * A1  score_multi_vector_masked -- general exact path (evaluator/retrieval.py:166-213)
+ *
+ *   out[q,c] = has[c] * sum_n qmask[q,n] * max_m ( pmask[c,m] ? <Q[q,n,:],P[c,m,:]> : -1e4 )
+ *
+ * fp32 FMA accumulation on the operands as given (bf16 inputs are up-cast like the
+ * reference's `.to(float32)`, :176-177).  Any nq, np, lq, lp >= 1 and d % 4 == 0,
+ * arbitrary mask patterns (uint8, non-zero = valid).  `argmax_dev` (optional,
+ * int32, PAGE-MAJOR [np, nq*lq]) receives the lowest page-token index attaining
+ * each max (torch.max's tie rule), for the backward.  `rowmax_ws_dev` is
+ * caller-provided scratch of np*nq*lq floats (same layout).  np <= 65535 per call.
+ * ------------------------------------------------------------------------ */
+EVDR_API int evdr_maxsim_fwd(evdr_handle* h,
+                             const void* Q_dev, int q_dtype,
+                             const void* P_dev, int p_dtype,
+                             const uint8_t* qmask_dev, const uint8_t* pmask_dev,
+                             int nq, int np, int lq, int lp, int d,
+                             float* rowmax_ws_dev, int32_t* argmax_dev,
+                             float* out_dev, void* stream);
+
+/* A5  backward of A1 (autograd of evaluator/retrieval.py:166-213):
+ *   dP[c,m,:] = sum_{q,n} g[q,c] qmask[q,n] has[c] [m == argmax[q,c,n]] Q[q,n,:]
+ *   dQ[q,n,:] = sum_c     g[q,c] qmask[q,n] has[c] P[c, argmax[q,c,n], :]
+ * Deterministic (no floating-point atomics): one CTA owns one page's dP tile and
+ * accumulates query tokens in index order.  dQ_dev may be NULL. */
+EVDR_API int evdr_maxsim_bwd(evdr_handle* h,
+                             const float* gout_dev,
+                             const void* Q_dev, int q_dtype,
+                             const void* P_dev, int p_dtype,
+                             const uint8_t* qmask_dev, const uint8_t* pmask_dev,
+                             const int32_t* argmax_dev,
+                             int nq, int np, int lq, int lp, int d,
+                             float* dP_dev, float* dQ_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Packed page stream (the HBM layout of the tensor-core path)
+ *
+ * evdr_pack_plan: chunk_off[c] = first 16-token chunk of page c in the stream,
+ *   chunk_off[np] = total chunks.  varlen == 0: every page gets ceil(lp/16)
+ *   chunks (offsets are arithmetic, no host sync needed to size the stream);
+ *   varlen != 0: a page gets ceil((last valid index + 1)/16) chunks, at least 1.
+ * evdr_pack_pages: writes the bf16 stream.  Masked / padded slots inside a page's
+ *   chunks are filled with a copy of a valid token of the same page (nearest
+ *   preceding valid token, else the first valid one), so they can never change a
+ *   max; a page with no valid token becomes all-zero tokens (score exactly 0,
+ *   as evaluator/retrieval.py:192,204).  normalize != 0 fuses the reference's
+ *   `l2_normalize(P * pmask[...,None])` (utils/preprocess_data.py:8-9,
+ *   mainv2_iter_listwise.py:280) in fp32 before the bf16 rounding.
+ * ------------------------------------------------------------------------ */
+EVDR_API int evdr_pack_plan(evdr_handle* h, const uint8_t* pmask_dev, int np, int lp,
+                            int varlen, int32_t* chunk_off_dev, void* stream);
+EVDR_API int evdr_pack_pages(evdr_handle* h, const void* P_dev, int p_dtype,
+                             const uint8_t* pmask_dev, const int32_t* chunk_off_dev,
+                             int np, int lp, int d, int normalize,
+                             void* tokens_bf16_dev, void* stream);
+/* Queries for the tensor-core path: bf16 [nq, 32, 128], masked / padded token
+ * slots zeroed; qmask32 [nq, 32] uint8.  Requires lq <= 32, d == 128. */
+EVDR_API int evdr_pack_queries(evdr_handle* h, const void* Q_dev, int q_dtype,
+                               const uint8_t* qmask_dev, int nq, int lq, int d,
+                               void* Qb_bf16_dev, uint8_t* qmask32_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * A1 on tensor cores: TMA-fed bf16 tcgen05.mma with fp32 TMEM accumulators; the
+ * row-max over page tokens and the query-token sum are fused into the epilogue,
+ * the similarity matrix never leaves the SM.  Persistent kernel, one CTA per SM.
+ *
+ *   tokens_dev : bf16 [n_tokens, 128], n_tokens >= 16*chunk_off[np] (the stream);
+ *   Qb_dev     : bf16 [nq, 32, 128] from evdr_pack_queries;
+ *   out_dev    : fp32 [nq, out_ld], column c = page c.
+ * The base addresses must be 16-byte aligned (TMA).  `pages_per_item` <= 0 lets
+ * the library pick the work-item size.
+ * ------------------------------------------------------------------------ */
+EVDR_API int evdr_maxsim_packed_fwd(evdr_handle* h,
+                                    const void* Qb_dev, const uint8_t* qmask32_dev, int nq,
+                                    const void* tokens_dev, int64_t n_tokens,
+                                    const int32_t* chunk_off_dev, int np,
+                                    int64_t total_chunks, int pages_per_item,
+                                    float* out_dev, int64_t out_ld, void* stream);
+
+/* ------------------------------------------------------------------------
+ * A7  evaluation tail: top-k and trec_eval-style measures on device
+ * (replaces the Nq*Np `.item()` dict build of mainv2_iter_listwise.py:312-318 and
+ * mteb/pytrec_eval behind evaluator/retrieval.py:239-246).
+ *
+ * evdr_topk: per query the k best columns of scores[nq, ld] (first np columns),
+ *   ordered by score descending, ties by tie_rank[c] ascending when given (host
+ *   passes the rank of the docid string in DESCENDING order to reproduce
+ *   trec_eval), else by column index ascending.  ids are column + id_offset.
+ *   Slots beyond np are (-inf, -1).  1 <= k <= 128.
+ * evdr_topk_merge: same selection over explicit (score, id) candidate lists
+ *   (ties by id ascending) -- the merge step after the all-gather.
+ * evdr_retrieval_metrics: out[m][j][q] for m in {ndcg, map, recall, precision,
+ *   mrr}, j over k_values, from ranked ids [nq, kmax] and CSR qrels (ids within a
+ *   query need not be sorted).  Linear gain, log2 discount, double accumulators
+ *   like trec_eval; the host takes the mean and round(., 5) like mteb.
+ * ------------------------------------------------------------------------ */
+EVDR_API int evdr_topk(evdr_handle* h, const float* scores_dev, int64_t ld, int nq, int np,
+                       int k, const int32_t* tie_rank_dev, int64_t id_offset,
+                       float* top_scores_dev, int64_t* top_ids_dev, void* stream);
+EVDR_API int evdr_topk_merge(evdr_handle* h, const float* cand_scores_dev,
+                             const int64_t* cand_ids_dev, int nq, int ncand, int k,
+                             float* top_scores_dev, int64_t* top_ids_dev, void* stream);
+EVDR_API int evdr_retrieval_metrics(evdr_handle* h, const int64_t* top_ids_dev, int kmax, int nq,
+                                    const int32_t* qrel_off_dev, const int64_t* qrel_ids_dev,
+                                    const int32_t* qrel_rels_dev,
+                                    const int32_t* k_values_dev, int nk,
+                                    double* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU: pages sharded by contiguous range, queries replicated.  Each rank
+ * runs its local scan + evdr_topk, then one ncclAllGather of nq*k (score, id)
+ * pairs and a merge on every rank (identical result everywhere).
+ * NCCL is resolved at run time from the process (torch's libnccl.so.2).
+ * ------------------------------------------------------------------------ */
+#define EVDR_NCCL_UNIQUE_ID_BYTES 128
+EVDR_API int evdr_comm_unique_id(void* id_out_128B);
+EVDR_API int evdr_comm_init(evdr_handle* h, const void* id_128B, int rank, int world);
+EVDR_API int evdr_comm_world(const evdr_handle* h);
+/* Scratch for the exchange is stream-ordered (cudaMallocAsync on `stream`). */
+EVDR_API int evdr_sharded_topk(evdr_handle* h, const float* local_scores_dev, int64_t ld,
+                               int nq, int np_local, int k, int64_t id_offset,
+                               float* top_scores_dev, int64_t* top_ids_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * A4  fused mask * l2_normalize (utils/preprocess_data.py:8-9 applied as
+ * mainv2_iter_listwise.py:280) and its backward, fp32:
+ *   y = (x*mask) / (||x*mask||_2 + 1e-12)
+ * ------------------------------------------------------------------------ */
+EVDR_API int evdr_l2norm_fwd(evdr_handle* h, const float* X_dev, const uint8_t* mask_dev,
+                             int64_t n_tok, int d, float* Y_dev, void* stream);
+EVDR_API int evdr_l2norm_bwd(evdr_handle* h, const float* X_dev, const uint8_t* mask_dev,
+                             const float* gY_dev, int64_t n_tok, int d, float* gX_dev,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVDR_H_ */
