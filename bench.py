@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- MaxSim query-page pairs/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: 1024 queries (32 tokens, 128-d) scored against
+this rank's 100 000-page shard (1030 valid tokens per page, stored as 1040 bf16 slots) with the
+tcgen05 MaxSim kernel, followed by the local top-10 and -- for N > 1 -- the NCCL all-gather + merge
+of the candidates (BASELINE.json configs[2] per GPU; the corpus grows with N: weak scaling).
+
+value     : whole-job pairs/s with everything resident in HBM (CUDA events, max over ranks)
+e2e       : same metric through the reference-facing call score_multi_vector_masked(Q, P, qmask,
+            pmask) with the query batch copied from pinned host memory and the (nq, np) score matrix
+            read back to the host inside the timed region, every step
+roofline  : dominant kernel (maxsim_tc_kernel) alone: algorithmic FLOPs / CUDA-event duration vs the
+            measured bf16 peak of MEASURED_PEAKS.json
+cpu_baseline / --impl reference : the reference's algorithm (oracle port, torch CPU, all host
+            threads) on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D = 128
+LQ = 32
+LP_VALID = 1030          # ColPali tokens per page
+LP_SLOTS = 1040          # 65 chunks of 16
+TOPK = 10
+FLOPS_PER_PAIR = 2 * D * LQ * LP_VALID          # 8 437 760 (padding not counted)
+BYTES_PER_PAGE = LP_VALID * D * 2               # 263 680
+METRIC = "maxsim_query_page_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "source": "measured"}
+    # fallback stated by /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_rate(seconds_target: float = 12.0, n_queries: int = 32):
+    """Reference algorithm (oracle port of evaluator/retrieval.py:166-213, torch CPU, fp32, chunk_p=64)
+    on a bounded sample of the workload: n_queries x S pages of 1030 tokens."""
+    import torch
+    from oracle.maxsim_oracle import maxsim_masked_torch_cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(42)
+    def sample(n_pages):
+        P = torch.nn.functional.normalize(torch.randn(n_pages, LP_VALID, D, generator=g), dim=-1)
+        Q = torch.nn.functional.normalize(torch.randn(n_queries, LQ, D, generator=g), dim=-1)
+        return Q, P, torch.ones(n_queries, LQ, dtype=torch.bool), torch.ones(n_pages, LP_VALID, dtype=torch.bool)
+    Q, P, qm, pm = sample(64)
+    maxsim_masked_torch_cpu(Q, P, qm, pm, 64)                      # warm-up
+    t0 = time.perf_counter()
+    maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
+    rate = n_queries * 64 / (time.perf_counter() - t0)
+    n_pages = int(max(64, min(4096, (rate * seconds_target / n_queries) // 64 * 64)))
+    Q, P, qm, pm = sample(n_pages)
+    t0 = time.perf_counter()
+    maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
+    dt = time.perf_counter() - t0
+    return {"value": n_queries * n_pages / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_queries} queries x {n_pages} pages x {LP_VALID} tokens fp32, chunk_p=64, {dt:.2f} s"}, (Q, P, qm, pm)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port -- the
+    reference is pure Python and /root/reference does not exist on the GPU box) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.maxsim_oracle import maxsim_masked_torch_cpu
+    base, (Q, P, qm, pm) = cpu_reference_rate(seconds_target=max(2.0, 40.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = Q.shape[0] * P.shape[0] / dt
+    base["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"query-batched MaxSim: {args.queries} queries x {args.pages} pages per GPU "
+                    f"(BASELINE.json configs[2]), then top-{TOPK}"
+                    + (" + NCCL all-gather merge" if n_gpus > 1 else ""),
+        "queries": args.queries, "pages_per_gpu": args.pages, "pages_total": args.pages * n_gpus,
+        "tokens_per_page": LP_VALID, "token_slots_per_page": LP_SLOTS, "query_tokens": LQ, "dim": D,
+        "top_k": TOPK, "parallelism": f"page-sharded x{n_gpus}, queries replicated",
+        "l2": f"inputs larger than L2 ({args.pages * LP_SLOTS * D * 2 / 1e9:.1f} GB corpus per GPU vs 126 MB)",
+    }
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pages", type=int, default=100_000, help="pages per GPU")
+    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-query / 64-query side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import evdr_b200 as evdr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        evdr.init_nccl_comm(dev)
+    n_gpus = world
+    peaks = load_peaks()
+
+    # ---- synthetic shard, generated on the device (never staged through host memory)
+    npg, nq = args.pages, args.queries
+    corpus = evdr.synth.make_uniform_corpus(npg, LP_SLOTS, device=dev, seed=42 + 1000 * rank)
+    corpus[:, LP_VALID:] = corpus[:, LP_VALID - 1:LP_VALID]       # filler slots duplicate a valid token
+    pmask = torch.ones((npg, LP_SLOTS), dtype=torch.bool, device=dev)
+    pk = evdr.PackedPages.from_uniform_tokens(corpus, page_offset=rank * npg)
+    gq = torch.Generator().manual_seed(43)                           # identical queries on every rank
+    Qh = torch.nn.functional.normalize(torch.randn(nq, LQ, D, generator=gq), dim=-1).bfloat16().float().pin_memory()
+    qmh = torch.ones((nq, LQ), dtype=torch.bool).pin_memory()
+    Q = Qh.to(dev)
+    qm = qmh.to(dev)
+    scores = torch.empty((nq, npg), dtype=torch.float32, device=dev)
+    search = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode="nccl")
+
+    def step():
+        Qb, qm32 = evdr.pack_queries(Q, qm)                          # 1 launch
+        pk.score_packed(Qb, qm32, out=scores)                        # 1 launch (maxsim_tc_kernel)
+        return search.topk(scores, TOPK)                             # 2 launches (+2 and the all-gather for N>1)
+
+    launches_per_step = 4 if n_gpus == 1 else 6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    pairs_per_step = nq * npg * n_gpus
+    value = pairs_per_step / (ms_step * 1e-3)
+
+    # ---- end to end through the reference-facing call, host buffers in the timed region
+    host_scores = torch.empty((nq, npg), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        Qd = Qh.to(dev, non_blocking=True)
+        qd = qmh.to(dev, non_blocking=True)
+        s = evdr.score_multi_vector_masked(Qd, corpus, qd, pmask, 64)     # drop-in signature
+        host_scores.copy_(s, non_blocking=True)
+
+    ms_e2e = timed(e2e_step, args.steps, args.warmup)
+    e2e = {"value": pairs_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": Qh.numel() * 4 + qmh.numel(), "d2h_bytes_per_step": host_scores.numel() * 4,
+           "call": "score_multi_vector_masked(Q, P, qmask, pmask, 64); page tensor resident on the device "
+                   "as in the reference (mainv2_iter_listwise.py:96), queries from pinned host memory, "
+                   "full (nq, np) score matrix read back"}
+
+    # ---- roofline of the dominant kernel, timed alone on its launch stream
+    Qb, qm32 = evdr.pack_queries(Q, qm)
+    ms_kernel = timed(lambda: pk.score_packed(Qb, qm32, out=scores), args.steps, 1)
+    flops = nq * npg * FLOPS_PER_PAIR
+    achieved = flops / (ms_kernel * 1e-3) / 1e12
+    roofline = {"kernel": "maxsim_tc_kernel", "bound": "tensor", "achieved": achieved,
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"],
+                "peak_kind": f"{peaks['source']} sustained cuBLAS bf16 (each launch runs {ms_kernel:.0f} ms, power-capped regime)",
+                "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "burst_peak": peaks["bf16_tflops"],
+                "ms_per_launch": ms_kernel, "algorithmic_flops_per_launch": flops, "traffic": None}
+
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras = side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus)
+        except Exception as e:  # side numbers must never lose the headline line
+            extras = {"error": repr(e)}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                cpu, _ = cpu_reference_rate()
+            except Exception as e:
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, n_gpus),
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+            "peaks": peaks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus):
+    """Single-query streaming scan (HBM-bound) and 64-query batches (BASELINE.json configs[3])."""
+    out = {}
+    npg = pk.n_pages
+    for nq in (1, 64):
+        g = torch.Generator().manual_seed(50 + nq)
+        Q = torch.nn.functional.normalize(torch.randn(nq, LQ, D, generator=g), dim=-1).to(dev)
+        qm = torch.ones((nq, LQ), dtype=torch.bool, device=dev)
+        Qb, qm32 = evdr.pack_queries(Q, qm)
+        s = torch.empty((nq, npg), dtype=torch.float32, device=dev)
+        ms_scan = timed(lambda: pk.score_packed(Qb, qm32, out=s), 10, 3)
+        ms_search = timed(lambda: search.topk(pk.score_packed(Qb, qm32, out=s), TOPK), 10, 3)
+        pages_s = npg / (ms_scan * 1e-3)
+        rec = {"ms_scan": ms_scan, "ms_search_top10": ms_search, "pages_per_s_per_gpu": pages_s,
+               "pairs_per_s": nq * npg * n_gpus / (ms_search * 1e-3),
+               "queries_per_s_at_this_corpus": nq / (ms_search * 1e-3), "pages_total": npg * n_gpus}
+        if nq == 1:
+            gbs = pages_s * BYTES_PER_PAGE / 1e9
+            rec["roofline"] = {"kernel": "maxsim_tc_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+        else:
+            tf = nq * npg * FLOPS_PER_PAIR / (ms_scan * 1e-3) / 1e12
+            rec["roofline"] = {"kernel": "maxsim_tc_kernel", "bound": "tensor", "achieved": tf,
+                               "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"]}
+        out[f"q{nq}"] = rec
+    return out
+
+
+if __name__ == "__main__":
+    main()

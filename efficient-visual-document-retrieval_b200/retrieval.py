@@ -142,7 +142,11 @@ def _packed_for(P: torch.Tensor, pmask: torch.Tensor) -> PackedPages:
     if hit is not None:
         _PACK_CACHE.move_to_end(key)
         return hit
-    pk = PackedPages.from_padded(P, pmask, normalize=False, varlen=False)
+    if (P.dtype == torch.bfloat16 and P.is_contiguous() and P.shape[1] % _lib.CHUNK == 0
+            and bool(pmask.all().item())):
+        pk = PackedPages.from_uniform_tokens(P)        # already in stream layout: used in place
+    else:
+        pk = PackedPages.from_padded(P, pmask, normalize=False, varlen=False)
     if _PACK_CACHE_SLOTS > 0:
         # hold references so that the key's storage cannot be recycled while cached
         pk._key_refs = (P, pmask)
