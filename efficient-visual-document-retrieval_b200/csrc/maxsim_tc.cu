@@ -233,34 +233,66 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             tc_fence_after();
             const uint32_t t_addr = t_lane + buf * BN;
             float rm = runmax[r];
+            // page complete for this query tile: mask, reduce the 32 query tokens, store, next page
+            auto finalize = [&]() {
+              const float s = warp_sum(rm * qm[r]);
+              if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
+              rm = -INFINITY;
+              ++p;
+              const int b = (p - p0) >> 5;
+              if (b != cb) { cb = b; pe_cache = load_pe(b); }
+              pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
+            };
+            if (pe >= ch_tile0 + CH_PER_TILE) {
+              // ---- fast path: the whole tile belongs to the current page.  TMEM loads are
+              // double-buffered in registers so that the next 32 columns are in flight while the
+              // current 32 go through the FMNMX3 tree.
+              float va[32], vb[32];
+              tmem_ld32_issue(t_addr, va);
+              tmem_wait_ld_tied(va);
+#pragma unroll
+              for (int grp = 0; grp < BN / 32; grp += 2) {
+                tmem_ld32_issue(t_addr + (grp + 1) * 32, vb);
+                rm = max_tree32(rm, va);
+                tmem_wait_ld_tied(vb);
+                if (grp + 2 < BN / 32) {
+                  tmem_ld32_issue(t_addr + (grp + 2) * 32, va);
+                } else {
+                  // last TMEM read of this buffer is complete: hand it back to the MMA warp early
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bar_t_empty(buf));
+                }
+                rm = max_tree32(rm, vb);
+                if (grp + 2 < BN / 32) tmem_wait_ld_tied(va);
+              }
+              if (pe == ch_tile0 + CH_PER_TILE) finalize();
+            } else {
+              // ---- boundary path: a page ends inside the tile (or the item ends): 32 columns
+              // (two chunks) at a time, page ends can fall after either chunk
 #pragma unroll 1
-            for (int grp = 0; grp < BN / 32; ++grp) {
-              const int ch = ch_tile0 + grp * 2;
-              if (ch >= nch) break;
-              float v[32];
-              tmem_ld32_wait(t_addr + grp * 32, v);
-#pragma unroll
-              for (int hc = 0; hc < 2; ++hc) {
-                if (ch + hc < nch) {
-#pragma unroll
-                  for (int i = 0; i < 16; i += 2) rm = max3(rm, v[hc * 16 + i], v[hc * 16 + i + 1]);
-                  if (ch + hc + 1 == pe) {
-                    // page complete for this query tile: mask, reduce the 32 query tokens, store
-                    float s = warp_sum(rm * qm[r]);
-                    if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
-                    rm = -INFINITY;
-                    ++p;
-                    const int b = (p - p0) >> 5;
-                    if (b != cb) { cb = b; pe_cache = load_pe(b); }
-                    pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
+              for (int grp = 0; grp < BN / 32; ++grp) {
+                const int ch = ch_tile0 + grp * 2;
+                if (ch >= nch) break;
+                float v[32];
+                tmem_ld32_wait(t_addr + grp * 32, v);
+                if (pe > ch + 1 && ch + 1 < nch) {        // both chunks belong to the current page
+                  rm = max_tree32(rm, v);
+                  if (pe == ch + 2) finalize();
+                } else {
+                  rm = max_tree16(rm, v, 0);
+                  if (pe == ch + 1) finalize();
+                  if (ch + 1 < nch) {
+                    rm = max_tree16(rm, v, 16);
+                    if (pe == ch + 2) finalize();
                   }
                 }
               }
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_t_empty(buf));
             }
             runmax[r] = rm;
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_t_empty(buf));
             ++acc_it;
           }
         }

@@ -36,13 +36,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or
+// the hint (ns) expires, instead of re-polling every ~50 ns and stealing issue slots from the
+// epilogue warp that shares its scheduler.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
 // Bounded wait: a pipeline bug traps (launch fails with an error) instead of hanging the GPU.
@@ -52,8 +55,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > EVDR_WATCHDOG_CYCLES) {
+    if ((++polls & 0x3ffu) == 0 && clock64() - t0 > EVDR_WATCHDOG_CYCLES) {
       printf("evdr: mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", blockIdx.x,
              threadIdx.x, bar, parity);
       __trap();
@@ -209,6 +213,29 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+
+// max(rm, v[0..31]) as a depth-4 tree of 3-input maxes: 16 FMNMX3 with one op on the rm chain
+__device__ __forceinline__ float max_tree32(float rm, const float (&v)[32]) {
+  float a[10];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) a[j] = max3(v[3 * j], v[3 * j + 1], v[3 * j + 2]);
+  const float b0 = max3(a[0], a[1], a[2]);
+  const float b1 = max3(a[3], a[4], a[5]);
+  const float b2 = max3(a[6], a[7], a[8]);
+  const float b3 = max3(a[9], v[30], v[31]);
+  return max3(rm, max3(b0, b1, b2), b3);
+}
+// max(rm, v[o..o+15]): 8 FMNMX3, depth 3
+__device__ __forceinline__ float max_tree16(float rm, const float (&v)[32], int o) {
+  const float a0 = max3(v[o + 0], v[o + 1], v[o + 2]);
+  const float a1 = max3(v[o + 3], v[o + 4], v[o + 5]);
+  const float a2 = max3(v[o + 6], v[o + 7], v[o + 8]);
+  const float a3 = max3(v[o + 9], v[o + 10], v[o + 11]);
+  const float a4 = max3(v[o + 12], v[o + 13], v[o + 14]);
+  const float b0 = max3(a0, a1, a2);
+  const float b1 = max3(a3, a4, v[o + 15]);
+  return max3(rm, b0, b1);
 }
 
 // ---------------------------------------------------------------- descriptors
