@@ -8,16 +8,25 @@
 // Structure: persistent, warp-specialised, one CTA per SM, 192 threads:
 //   warp 0      TMA producer  : cp.async.bulk.tensor of query tiles (A, resident) and page-token
 //                               tiles (B, STAGES-deep ring) into 128B-swizzled shared memory
-//   warp 1      MMA issuer    : one thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16 x 8),
-//                               fp32 accumulators double-buffered in TMEM (2 x BN columns)
-//   warps 2..5  epilogue      : tcgen05.ld 32 columns at a time; lane = query token, so the max over
-//                               page tokens is a per-thread running FMNMX3 chain; at a page's last
-//                               chunk: * qmask, warp-shuffle sum over the 32 tokens of the query,
-//                               one fp32 store.  The similarity matrix never leaves the SM.
+//   warp 1      MMA issuer    : one thread issues tcgen05.mma.kind::f16 (K=16 x 8 per tile), fp32
+//                               accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 2..5  epilogue      : tcgen05.ld 32 columns at a time (double-buffered in registers);
+//                               lane = query token, so the max over page tokens is a per-thread
+//                               FMNMX3 tree; at a page's last chunk: * qmask, warp-shuffle sum over the
+//                               32 tokens of the query, one fp32 store.  The similarity matrix never
+//                               leaves the SM.
 //
-// Work item = (page block pb, query group g): R resident A tiles (4 queries each) x all B tiles of
-// the block.  Items are ordered g-fastest and dealt round-robin to CTAs so that concurrently
-// running CTAs read the same page block (L2 hit) and HBM sees every page once.
+// Two flavours of the same kernel:
+//   CG2 = false : one CTA per tile, tcgen05.mma.cta_group::1, M = 128 x N = 256.  Used for a single
+//                 query tile (<= 4 queries): the HBM-bound streaming scan.
+//   CG2 = true  : CTA pairs (cluster of 2), tcgen05.mma.cta_group::2, M = 256 x N = 256: each CTA
+//                 holds its own 128 query-token rows and HALF of the page tile, so the shared-memory
+//                 operand traffic per SM drops from 96 to 64 B/clk and the L2->SM page traffic
+//                 halves.  Used for batched scoring (tensor-bound).
+//
+// Work item = (page block pb, query group g): R resident A tiles per CTA x all B tiles of the block.
+// Items are ordered g-fastest and dealt round-robin to CTAs (pairs) so that concurrently running
+// CTAs read the same page block (L2 hit) and HBM sees every page about once.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -38,31 +47,34 @@ struct TcParams {
   int nqt;                    // ceil(nq / 4) A tiles
   int ppi;                    // pages per item
   int n_pblocks, n_qgroups;
+  int g_base, g_rem;          // query tiles per group: g_base (+1 for the first g_rem groups)
   int stream_hint;            // 1: page tiles are read once (evict-first)
 };
 
-template <int R, int BN, int STAGES>
-struct TcSmem {
-  static constexpr int B_STAGE_BYTES = BN * 128 * 2;
-  static constexpr int B_HALF_BYTES = BN * 64 * 2;
+template <int R, int BN, int STAGES, bool CG2>
+struct TcCfg {
+  static constexpr int B_ROWS = CG2 ? BN / 2 : BN;          // page tokens held by this CTA per stage
+  static constexpr int B_HALF_BYTES = B_ROWS * 64 * 2;       // one 64-wide K half
+  static constexpr int B_STAGE_BYTES = 2 * B_HALF_BYTES;
   static constexpr int A_BYTES = R * A_TILE_BYTES;
   static constexpr int B_BYTES = STAGES * B_STAGE_BYTES;
   static constexpr int BAR_OFF = A_BYTES + B_BYTES;
   // barriers: full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2], tmem ptr
   static constexpr int BAR_BYTES = 8 * (2 * STAGES + 6) + 8;
   static constexpr int TOTAL = BAR_OFF + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TILES_PER_GROUP = CG2 ? 2 * R : R;
 };
 
-template <int R, int BN, int STAGES>
+template <int R, int BN, int STAGES, bool CG2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                  const TcParams prm) {
-  using S = TcSmem<R, BN, STAGES>;
+  using S = TcCfg<R, BN, STAGES, CG2>;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                             : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
-  constexpr uint32_t IDESC = make_idesc_bf16(128, BN);
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
+  constexpr uint32_t IDESC = make_idesc_bf16(CG2 ? 256 : 128, BN);
   constexpr int CH_PER_TILE = BN / EVDR_CHUNK;
 
   extern __shared__ uint8_t smem_raw[];
@@ -82,6 +94,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CG2 ? (int)cluster_ctarank() : 0;            // 0 = leader of the CTA pair
+  const int unit = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmapQ);
@@ -89,62 +104,90 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     mbar_init(bar_a_full, 1);
     mbar_init(bar_a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full(b), 1); mbar_init(bar_t_empty(b), 4); }
+    // tmem_empty lives in the leader: 4 epilogue warps of each CTA of the pair arrive on it
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full(b), 1); mbar_init(bar_t_empty(b), CG2 ? 8 : 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_items = prm.n_pblocks * prm.n_qgroups;
+  // query tiles are dealt to the groups as evenly as possible (sizes differ by at most one), so
+  // that the static round-robin item schedule stays balanced
+  auto group_start = [&](int g) { return g * prm.g_base + min(g, prm.g_rem); };
+  auto group_size = [&](int g) { return prm.g_base + (g < prm.g_rem ? 1 : 0); };
+  // passes (query tiles of this CTA) in group g
+  auto passes_in_group = [&](int g) { return CG2 ? (group_size(g) + 1) >> 1 : group_size(g); };
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (each CTA loads its own
+    // query tiles and its half of the page tile; in pair mode all bytes are counted on the
+    // LEADER's barriers, which the MMA issuer waits on)
     if (lane == 0) {
       const uint64_t pol = prm.stream_hint ? policy_evict_first() : policy_evict_last();
       int stage = 0, phase = 0, a_loads = 0, cur_g = -1;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const uint32_t a_full_tx = CG2 ? mapa_u32(bar_a_full, 0) : bar_a_full;
+      for (int it = unit; it < n_items; it += n_units) {
         const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
         const int p0 = pb * prm.ppi, p1 = min(p0 + prm.ppi, prm.np);
         const int c0 = prm.chunk_off[p0], c1 = prm.chunk_off[p1];
         const int ntile = ((c1 - c0) * EVDR_CHUNK + BN - 1) / BN;
-        const int qt0 = g * R;
-        const int rc = min(R, prm.nqt - qt0);
+        const int rc = passes_in_group(g);
         if (g != cur_g) {
           if (a_loads > 0) mbar_wait(bar_a_empty, (a_loads - 1) & 1);
-          mbar_expect_tx(bar_a_full, rc * A_TILE_BYTES);
+          // out-of-range query tiles are zero-filled by TMA and still count their bytes
+          if (rank == 0) mbar_expect_tx(bar_a_full, (CG2 ? 2 : 1) * rc * A_TILE_BYTES);
           for (int r = 0; r < rc; ++r) {
-            tma_load_2d(sA + r * A_TILE_BYTES, &tmapQ, bar_a_full, 0, (qt0 + r) * 128);
-            tma_load_2d(sA + r * A_TILE_BYTES + A_HALF_BYTES, &tmapQ, bar_a_full, 64, (qt0 + r) * 128);
+            const int tile = group_start(g) + (CG2 ? 2 * r + rank : r);
+            if constexpr (CG2) {
+              tma_load_2d_cg2(sA + r * A_TILE_BYTES, &tmapQ, a_full_tx, 0, tile * 128);
+              tma_load_2d_cg2(sA + r * A_TILE_BYTES + A_HALF_BYTES, &tmapQ, a_full_tx, 64, tile * 128);
+            } else {
+              tma_load_2d(sA + r * A_TILE_BYTES, &tmapQ, a_full_tx, 0, tile * 128);
+              tma_load_2d(sA + r * A_TILE_BYTES + A_HALF_BYTES, &tmapQ, a_full_tx, 64, tile * 128);
+            }
           }
           ++a_loads;
           cur_g = g;
         }
         for (int t = 0; t < ntile; ++t) {
           mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_expect_tx(bar_full(stage), S::B_STAGE_BYTES);
-          const int row = c0 * EVDR_CHUNK + t * BN;
-          tma_load_2d_hint(sB + stage * S::B_STAGE_BYTES, &tmapP, bar_full(stage), 0, row, pol);
-          tma_load_2d_hint(sB + stage * S::B_STAGE_BYTES + S::B_HALF_BYTES, &tmapP, bar_full(stage), 64, row, pol);
+          if (rank == 0) mbar_expect_tx(bar_full(stage), (CG2 ? 2 : 1) * S::B_STAGE_BYTES);
+          const int row = c0 * EVDR_CHUNK + t * BN + rank * S::B_ROWS;
+          const uint32_t dst = sB + stage * S::B_STAGE_BYTES;
+          if constexpr (CG2) {
+            const uint32_t full_tx = mapa_u32(bar_full(stage), 0);
+            tma_load_2d_cg2_hint(dst, &tmapP, full_tx, 0, row, pol);
+            tma_load_2d_cg2_hint(dst + S::B_HALF_BYTES, &tmapP, full_tx, 64, row, pol);
+          } else {
+            tma_load_2d_hint(dst, &tmapP, bar_full(stage), 0, row, pol);
+            tma_load_2d_hint(dst + S::B_HALF_BYTES, &tmapP, bar_full(stage), 64, row, pol);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (one thread, leader CTA)
+    if (lane == 0 && rank == 0) {
       int stage = 0, phase = 0, a_phase = 0, cur_g = -1;
       uint32_t acc_it = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      auto commit = [&](uint32_t bar) {
+        if constexpr (CG2) mma_commit_cg2_mc(bar, (uint16_t)0x3); else mma_commit(bar);
+      };
+      for (int it = unit; it < n_items; it += n_units) {
         const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
         const int p0 = pb * prm.ppi, p1 = min(p0 + prm.ppi, prm.np);
         const int c0 = prm.chunk_off[p0], c1 = prm.chunk_off[p1];
         const int ntile = ((c1 - c0) * EVDR_CHUNK + BN - 1) / BN;
-        const int rc = min(R, prm.nqt - g * R);
+        const int rc = passes_in_group(g);
         if (g != cur_g) {
-          if (cur_g != -1) mma_commit(bar_a_empty);  // previous A tiles free once their MMAs retire
+          if (cur_g != -1) commit(bar_a_empty);  // previous A tiles free once their MMAs retire
           mbar_wait(bar_a_full, a_phase);
           a_phase ^= 1;
           tc_fence_after();
@@ -164,12 +207,13 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             for (int k = 0; k < 8; ++k) {
               const uint64_t da = make_sw128_desc(a_base + (k >> 2) * A_HALF_BYTES + (k & 3) * 32);
               const uint64_t db = make_sw128_desc(b_base + (k >> 2) * S::B_HALF_BYTES + (k & 3) * 32);
-              mma_bf16_ss(d_tmem, da, db, IDESC, k > 0);
+              if constexpr (CG2) mma_bf16_ss_cg2(d_tmem, da, db, IDESC, k > 0);
+              else mma_bf16_ss(d_tmem, da, db, IDESC, k > 0);
             }
-            mma_commit(bar_t_full(buf));
+            commit(bar_t_full(buf));
             ++acc_it;
           }
-          mma_commit(bar_empty(stage));  // page tile consumed by all R query tiles
+          commit(bar_empty(stage));  // page tile consumed by all resident query tiles
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -184,19 +228,31 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     int qidx[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { qm[r] = 0.f; qidx[r] = -1; }
+    const uint32_t t_empty0 = CG2 ? mapa_u32(bar_t_empty(0), 0) : bar_t_empty(0);
+    const uint32_t t_empty1 = CG2 ? mapa_u32(bar_t_empty(1), 0) : bar_t_empty(1);
+    auto release_tmem = [&](int buf) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t a = buf ? t_empty1 : t_empty0;
+        if constexpr (CG2) mbar_arrive_remote(a); else mbar_arrive(a);
+      }
+    };
 
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int it = unit; it < n_items; it += n_units) {
       const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
       const int p0 = pb * prm.ppi, p1 = min(p0 + prm.ppi, prm.np);
       const int c0 = prm.chunk_off[p0], c1 = prm.chunk_off[p1];
       const int nch = c1 - c0;
       const int ntile = (nch * EVDR_CHUNK + BN - 1) / BN;
-      const int rc = min(R, prm.nqt - g * R);
+      const int rc = passes_in_group(g);
       if (g != cur_g) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int q = (g * R + r) * 4 + quad;
-          const bool ok = (r < rc) && (q < prm.nq);
+          const int tile = group_start(g) + (CG2 ? 2 * r + rank : r);
+          const int q = tile * 4 + quad;
+          // in pair mode the peer's last tile of an odd-sized group belongs to the next group
+          const bool ok = (r < rc) && (tile < group_start(g) + group_size(g)) && (q < prm.nq);
           qidx[r] = ok ? q : -1;
           qm[r] = ok ? (float)prm.qmask32[(size_t)q * EVDR_TC_LQ + lane] : 0.f;
         }
@@ -205,8 +261,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       // page-end cache: lane l holds the (item-relative) end chunk of page p0 + 32*cb + l
       int cb = 0;
       auto load_pe = [&](int b) {
-        const int p = p0 + 32 * b + lane;
-        return (p < p1) ? (prm.chunk_off[p + 1] - c0) : 0x7fffffff;
+        const int pp = p0 + 32 * b + lane;
+        return (pp < p1) ? (prm.chunk_off[pp + 1] - c0) : 0x7fffffff;
       };
       int pe_cache = load_pe(0);
       int p = p0;                     // current page
@@ -243,54 +299,49 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               if (b != cb) { cb = b; pe_cache = load_pe(b); }
               pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
             };
-            if (pe >= ch_tile0 + CH_PER_TILE) {
-              // ---- fast path: the whole tile belongs to the current page.  TMEM loads are
-              // double-buffered in registers so that the next 32 columns are in flight while the
-              // current 32 go through the FMNMX3 tree.
+            // ---- drain: per-chunk (16-column) maxes of this tile into registers.  TMEM loads are
+            // double-buffered in registers: the next 32 columns are in flight while the current 32
+            // go through the FMNMX3 trees.  The buffer goes back to the MMA warp as soon as the
+            // last load has landed, before any page logic.
+            float h[CH_PER_TILE];
+            {
               float va[32], vb[32];
               tmem_ld32_issue(t_addr, va);
               tmem_wait_ld_tied(va);
 #pragma unroll
               for (int grp = 0; grp < BN / 32; grp += 2) {
                 tmem_ld32_issue(t_addr + (grp + 1) * 32, vb);
-                rm = max_tree32(rm, va);
+                h[2 * grp] = max16(va, 0);
+                h[2 * grp + 1] = max16(va, 16);
                 tmem_wait_ld_tied(vb);
-                if (grp + 2 < BN / 32) {
-                  tmem_ld32_issue(t_addr + (grp + 2) * 32, va);
-                } else {
-                  // last TMEM read of this buffer is complete: hand it back to the MMA warp early
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(bar_t_empty(buf));
-                }
-                rm = max_tree32(rm, vb);
+                if (grp + 2 < BN / 32) tmem_ld32_issue(t_addr + (grp + 2) * 32, va);
+                else release_tmem(buf);
+                h[2 * grp + 2] = max16(vb, 0);
+                h[2 * grp + 3] = max16(vb, 16);
                 if (grp + 2 < BN / 32) tmem_wait_ld_tied(va);
               }
+            }
+            // ---- fold the chunk maxes into the running per-page max; a page can end after any chunk
+            if (pe >= ch_tile0 + CH_PER_TILE) {
+              float m = rm;
+#pragma unroll
+              for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, h[j], h[j + 1]);
+              rm = m;
               if (pe == ch_tile0 + CH_PER_TILE) finalize();
             } else {
-              // ---- boundary path: a page ends inside the tile (or the item ends): 32 columns
-              // (two chunks) at a time, page ends can fall after either chunk
+              // compact (not unrolled) segment loop: ONE copy of finalize per resident tile keeps the
+              // kernel inside the instruction cache.  Segment [lo, hi) of this tile's chunks belongs
+              // to the current page; membership is a warp-uniform predicate per chunk register.
+              int lo = 0;
 #pragma unroll 1
-              for (int grp = 0; grp < BN / 32; ++grp) {
-                const int ch = ch_tile0 + grp * 2;
-                if (ch >= nch) break;
-                float v[32];
-                tmem_ld32_wait(t_addr + grp * 32, v);
-                if (pe > ch + 1 && ch + 1 < nch) {        // both chunks belong to the current page
-                  rm = max_tree32(rm, v);
-                  if (pe == ch + 2) finalize();
-                } else {
-                  rm = max_tree16(rm, v, 0);
-                  if (pe == ch + 1) finalize();
-                  if (ch + 1 < nch) {
-                    rm = max_tree16(rm, v, 16);
-                    if (pe == ch + 2) finalize();
-                  }
-                }
+              while (lo < CH_PER_TILE) {
+                const int hi = min(pe - ch_tile0, CH_PER_TILE);   // pe is INT_MAX past the item's end
+#pragma unroll
+                for (int j = 0; j < CH_PER_TILE; ++j)
+                  rm = (j >= lo && j < hi) ? fmaxf(rm, h[j]) : rm;
+                if (pe - ch_tile0 <= CH_PER_TILE) finalize();
+                lo = hi;
               }
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_t_empty(buf));
             }
             runmax[r] = rm;
             ++acc_it;
@@ -300,11 +351,14 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     }
   }
 
+  // teardown: in pair mode the peer's shared memory / TMEM must stay alive until both CTAs are done
+  // (multicast commits and remote arrives target it)
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    __syncwarp();
+    if constexpr (CG2) tmem_dealloc_cg2<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -323,24 +377,39 @@ static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uin
   return EVDR_OK;
 }
 
-template <int R, int BN, int STAGES>
+template <int R, int BN, int STAGES, bool CG2>
 static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens,
                      TcParams prm, cudaStream_t st) {
-  using S = TcSmem<R, BN, STAGES>;
+  using S = TcCfg<R, BN, STAGES, CG2>;
   CUtensorMap tmQ, tmP;
   int rc = encode_2d_bf16(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, 128, "queries");
   if (rc != EVDR_OK) return rc;
-  rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, BN, "page tokens");
+  rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, "page tokens");
   if (rc != EVDR_OK) return rc;
-  prm.n_qgroups = (prm.nqt + R - 1) / R;
-  auto kern = maxsim_tc_kernel<R, BN, STAGES>;
+  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2>;
   if ((size_t)S::TOTAL > h->smem_optin)
     return set_error(EVDR_ERR_UNSUPPORTED, "tensor-core kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const long long n_items = (long long)prm.n_pblocks * prm.n_qgroups;
-  const int grid = (int)(n_items < h->sm_count ? n_items : h->sm_count);
-  kern<<<grid, TC_THREADS, S::TOTAL, st>>>(tmQ, tmP, prm);
-  EVDR_LAUNCH_CHECK("maxsim_tc_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (CG2) {
+    const int pairs = h->sm_count / 2;
+    const int units = (int)(n_items < pairs ? n_items : pairs);
+    cfg.gridDim = dim3(2 * units);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((unsigned)(n_items < h->sm_count ? n_items : h->sm_count));
+  }
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  EVDR_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmP, prm));
   return EVDR_OK;
 }
 
@@ -370,24 +439,43 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
   prm.nq = nq;
   prm.np = np;
   prm.nqt = (nq + 3) / 4;
-  const int R = prm.nqt >= 3 ? 3 : prm.nqt;
-  const int n_qgroups = (prm.nqt + R - 1) / R;
+  // kernel flavour (EVDR_TC_MODE=pair selects the cta_group::2 kernels, for A/B runs)
+  const char* mode = getenv("EVDR_TC_MODE");
+  const bool want_pair = mode && strcmp(mode, "pair") == 0;
+  // single-CTA tiles are the default: measured 1443 vs 1282 TFLOP/s for CTA pairs at 1024 queries
+  // (profiles/): both are power-capped, the pair hand-offs cross the cluster and cost utilisation
+  const bool pair = want_pair && prm.nqt >= 2;
+  int R, tpg;
+  if (pair) { R = (prm.nqt + 1) / 2; if (R > 4) R = 4; tpg = 2 * R; }
+  else { R = prm.nqt >= 3 ? 3 : prm.nqt; tpg = R; }
+  const int n_qgroups = (prm.nqt + tpg - 1) / tpg;
+  const int units = pair ? h->sm_count / 2 : h->sm_count;
   int ppi = pages_per_item;
+  if (ppi <= 0) { const char* e = getenv("EVDR_TC_PPI"); if (e) ppi = atoi(e); }
   if (ppi <= 0) {
-    // ~16K tokens per item, tile-aligned for uniform pages; shrink while the grid is underfilled
+    // ~64K tokens per item (amortises the query-tile reload between items), tile-aligned for
+    // uniform pages; shrink while there are too few items to balance the grid
     const double avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
-    ppi = (int)(16384.0 / avg_tok + 0.5);
+    ppi = (int)(65536.0 / avg_tok + 0.5);
     if (ppi < 1) ppi = 1;
     if (ppi >= 16) ppi = (ppi / 16) * 16;
-    while (ppi > 1 && (long long)((np + ppi - 1) / ppi) * n_qgroups < 4LL * h->sm_count) ppi = (ppi + 1) / 2;
+    while (ppi > 1 && (long long)((np + ppi - 1) / ppi) * n_qgroups < 16LL * units) ppi = (ppi + 1) / 2;
   }
   if (ppi > np) ppi = np;
   prm.ppi = ppi;
   prm.n_pblocks = (np + ppi - 1) / ppi;
   prm.n_qgroups = n_qgroups;
+  prm.g_base = prm.nqt / n_qgroups;
+  prm.g_rem = prm.nqt % n_qgroups;
   prm.stream_hint = (n_qgroups == 1) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (R == 1) return launch_tc<1, 256, 3>(h, Qb, tokens, n_tokens, prm, st);
-  if (R == 2) return launch_tc<2, 256, 2>(h, Qb, tokens, n_tokens, prm, st);
-  return launch_tc<3, 256, 2>(h, Qb, tokens, n_tokens, prm, st);
+  if (pair) {
+    if (R == 1) return launch_tc<1, 256, 6, true>(h, Qb, tokens, n_tokens, prm, st);
+    if (R == 2) return launch_tc<2, 256, 5, true>(h, Qb, tokens, n_tokens, prm, st);
+    if (R == 3) return launch_tc<3, 256, 4, true>(h, Qb, tokens, n_tokens, prm, st);
+    return launch_tc<4, 256, 3, true>(h, Qb, tokens, n_tokens, prm, st);
+  }
+  if (R == 1) return launch_tc<1, 256, 3, false>(h, Qb, tokens, n_tokens, prm, st);
+  if (R == 2) return launch_tc<2, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
+  return launch_tc<3, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
 }

@@ -92,6 +92,34 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap*
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_cg2_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                     int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// ---------------------------------------------------------------- cluster
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+// arrive on an mbarrier given by a shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -225,6 +253,15 @@ __device__ __forceinline__ float max_tree32(float rm, const float (&v)[32]) {
   const float b2 = max3(a[6], a[7], a[8]);
   const float b3 = max3(a[9], v[30], v[31]);
   return max3(rm, max3(b0, b1, b2), b3);
+}
+// max(v[o..o+15]): 7 FMNMX3 + 1 FMNMX, depth 3
+__device__ __forceinline__ float max16(const float (&v)[32], int o) {
+  const float a0 = max3(v[o + 0], v[o + 1], v[o + 2]);
+  const float a1 = max3(v[o + 3], v[o + 4], v[o + 5]);
+  const float a2 = max3(v[o + 6], v[o + 7], v[o + 8]);
+  const float a3 = max3(v[o + 9], v[o + 10], v[o + 11]);
+  const float a4 = max3(v[o + 12], v[o + 13], v[o + 14]);
+  return fmaxf(max3(a0, a1, a2), max3(a3, a4, v[o + 15]));
 }
 // max(rm, v[o..o+15]): 8 FMNMX3, depth 3
 __device__ __forceinline__ float max_tree16(float rm, const float (&v)[32], int o) {
