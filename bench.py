@@ -40,6 +40,18 @@ LP_SLOTS = 1040          # 65 chunks of 16
 TOPK = 10
 FLOPS_PER_PAIR = 2 * D * LQ * LP_VALID          # 8 437 760 (padding not counted)
 BYTES_PER_PAGE = LP_VALID * D * 2               # 263 680
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 METRIC = "maxsim_query_page_pairs_per_sec"
 UNIT = "pairs/s"
 
@@ -159,7 +171,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n_gpus):
@@ -187,6 +199,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    # libraries (NCCL, torch) may print to stdout; keep fd 1 for the ONE JSON line only
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -312,7 +330,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
             "peaks": peaks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
