@@ -1,0 +1,129 @@
+"""GPU parity at the shapes of BASELINE.json's configs, against a plain PyTorch fp32 restatement of
+the op run on the same device (the reference's own eager path is the bar on a B200), and
+a training step through the exact kernels' backward (config 5)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_maxsim(Q, P, qmask, pmask, chunk=32):
+    """Plain torch fp32 MaxSim with the reference's semantics (evaluator/retrieval.py:166-213),
+    written for the tests: one matmul per page chunk, -1e4 fill, max, has-token and query masks, sum."""
+    Q, P = Q.float(), P.float()
+    qm, pm = qmask.bool(), pmask.bool()
+    outs = []
+    for s in range(0, P.shape[0], chunk):
+        Pc, mc = P[s:s + chunk], pm[s:s + chunk]
+        sim = torch.matmul(Q[:, None], Pc[None].transpose(-1, -2))          # (q, c, lq, lp)
+        sim = torch.where(mc[None, :, None, :], sim, sim.new_tensor(-1e4))
+        mx = sim.max(dim=-1).values * mc.any(1)[None, :, None] * qm[:, None, :]
+        outs.append(mx.sum(-1))
+    return torch.cat(outs, 1)
+
+
+# ViDoRe splits in the order of utils/mapping.py:2-91: (pages, queries); query counts are synthetic
+# choices; tatdqa's 1663 queries is the largest case.
+VIDORE = [("arxivqa", 500, 500), ("docvqa", 500, 500), ("infovqa", 500, 500), ("tabfquad", 70, 280),
+          ("tatdqa", 277, 1663), ("shift", 1000, 100), ("ai", 1000, 100), ("energy", 1000, 100),
+          ("gov", 1000, 100), ("health", 1000, 100)]
+
+
+@pytest.mark.parametrize("name,npg,nq", VIDORE)
+@pytest.mark.parametrize("lp", [1030, 64])
+def test_config2_vidore_shapes(evdr, cuda, name, npg, nq, lp):
+    """config 2: all ten splits, full 1030-token pages vs compressed 64-token pages, masked path."""
+    seed = 1000 + 2 * [v[0] for v in VIDORE].index(name) + (1 if lp == 64 else 0)
+    P, pm = evdr.synth.make_pages(npg, lp, seed=seed, device=cuda, n_holes=6 if lp > 64 else 2,
+                                  empty_frac=0.01, min_len=lp // 2)
+    Q, qm, rel = evdr.synth.make_queries(P, pm, nq, 32, seed=seed + 1, sigma=3.0 if lp > 64 else 1.5,
+                                         min_len=8, drop=0.1)
+    got = evdr.score_multi_vector_masked(Q, P, qm, pm, chunk_p=64)
+    # the full torch comparison materialises (q, c, 32, lp): check a slab of queries against it ...
+    qs = slice(0, min(nq, 48))
+    ref = torch_maxsim(Q[qs], P, qm[qs], pm)
+    U.assert_scores_close(got[qs].cpu().numpy(), ref.cpu().numpy())
+    # ... and everything against the exact fp32 kernels
+    exact = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
+    U.assert_scores_close(got.cpu().numpy(), exact.cpu().numpy())
+    # retrieval quality is identical: same top-1 wherever the margin exceeds the tolerance
+    top2 = exact.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 2e-3 * top2[:, 0].abs().clamp_min(1)
+    assert torch.equal(got.argmax(1)[clear], exact.argmax(1)[clear])
+
+
+def listwise_distillation_loss(score_s, score_t, k=10, temperature=1.0):
+    """criterion.py:114-142 restated for the test (the loss itself stays in torch)."""
+    score_t = score_t.detach()
+    log_ps = F.log_softmax(score_s / temperature, dim=1)
+    pt = F.softmax(score_t / temperature, dim=1)
+    _, idx = torch.topk(pt, k, dim=1)
+    return -(pt.gather(1, idx) * log_ps.gather(1, idx)).sum(1).mean() * temperature ** 2
+
+
+@pytest.mark.parametrize("npg,ls", [(500, 206), (1000, 41), (277, 21)])
+def test_config5_training_step(evdr, cuda, npg, ls):
+    """One optimisation step of mainv2_iter_liscore.py (:282-310): teacher scores (no grad, tcgen05),
+    student scores through l2_normalize(P*mask) with grad (exact kernels), listwise + MSE loss,
+    backward into the student parameter -- against the same step in plain torch."""
+    B = 32
+    Pt, pmt = evdr.synth.make_pages(npg, 1030, seed=1, device=cuda, empty_frac=0.0)
+    Q, qm, rel = evdr.synth.make_queries(Pt, pmt, B, 32, seed=2, sigma=3.0, min_len=10, drop=0.05)
+    g = torch.Generator(device=cuda).manual_seed(3)
+    Pbar = torch.randn(npg, ls, 128, generator=g, device=cuda)
+    pms = torch.rand(npg, ls, generator=g, device=cuda) > 0.1
+    pms[:, 0] = True
+
+    def step(score_fn, l2n):
+        param = Pbar.clone().requires_grad_(True)
+        Psb = l2n(param, pms)
+        with torch.no_grad():
+            sc_t = score_fn(Q, Pt, qm, pmt)
+        sc_s = score_fn(Q, Psb, qm, pms)
+        loss = listwise_distillation_loss(sc_s, sc_t, k=10, temperature=1.0) + F.mse_loss(sc_s, sc_t)
+        loss.backward()
+        return sc_t, sc_s.detach(), loss.detach(), param.grad
+
+    def l2n_torch(x, m):
+        x = x * m.unsqueeze(-1)
+        return x / (x.norm(dim=-1, keepdim=True) + 1e-12)
+
+    t_ref, s_ref, loss_ref, g_ref = step(torch_maxsim, l2n_torch)
+    t_got, s_got, loss_got, g_got = step(lambda *a: evdr.score_multi_vector_masked(*a, 64),
+                                         lambda x, m: evdr.l2_normalize_masked(x, m))
+    U.assert_scores_close(t_got.cpu().numpy(), t_ref.cpu().numpy())
+    np.testing.assert_allclose(s_got.cpu().numpy(), s_ref.cpu().numpy(), rtol=2e-5, atol=2e-5)
+    assert abs(loss_got.item() - loss_ref.item()) <= 2e-3 * max(1.0, abs(loss_ref.item()))
+    # masked student tokens receive exactly zero gradient (the invariant mainv1.py:74-87 prints)
+    assert g_got[~pms].abs().max() == 0
+    # gradients agree except where a near-tie picks another argmax token
+    num = (g_got - g_ref).norm()
+    den = g_ref.norm()
+    assert (num / den).item() < 2e-2, (num / den).item()
+    close = torch.isclose(g_got, g_ref, rtol=1e-3, atol=1e-6).float().mean().item()
+    assert close > 0.995, close
+
+
+def test_config1_docvqa_end_to_end(evdr, cuda):
+    """config 1: 500 queries x 500 pages, MaxSim + nDCG@5 through the evaluator on device vs the oracle's
+    trec restatement applied to plain-torch scores."""
+    from oracle import trec_oracle as to
+    P, pm = evdr.synth.make_pages(500, 1030, seed=11, device=cuda, n_holes=6, empty_frac=0.01)
+    Q, qm, rel = evdr.synth.make_queries(P, pm, 500, 32, seed=12, sigma=3.5, min_len=8, drop=0.1)
+    got = evdr.score_multi_vector_masked(Q, P, qm, pm, 64)
+    ref = torch.cat([torch_maxsim(Q[i:i + 50], P, qm[i:i + 50], pm) for i in range(0, 500, 50)])
+    U.assert_scores_close(got.cpu().numpy(), ref.cpu().numpy())
+    docs = [f"doc{c:04d}" for c in range(500)]
+    qrels = {f"q{q}": {docs[int(rel[q])]: 1} for q in range(500)}
+    refn, gotn = ref.cpu().numpy(), got.cpu().numpy()
+    res_ref = {f"q{q}": {docs[c]: float(refn[q, c]) for c in range(500)} for q in range(500)}
+    res_got = {f"q{q}": {docs[c]: float(gotn[q, c]) for c in range(500)} for q in range(500)}
+    want = to.compute_mteb_metrics(qrels, res_ref)
+    have = evdr.CustomRetrievalEvaluator().compute_mteb_metrics(qrels, res_got)
+    assert have["NDCG"]["NDCG@5"] == want["NDCG"]["NDCG@5"]
+    assert have["Recall"]["Recall@1"] == want["Recall"]["Recall@1"]
+    assert 0.3 < want["NDCG"]["NDCG@5"] < 1.0, want["NDCG"]
