@@ -17,7 +17,7 @@ from .normalize import l2_normalize, l2_normalize_masked
 from .retrieval import (BaseVisualRetrieverProcessor, CustomRetrievalEvaluator, maxsim_exact,
                         score_multi_vector_masked)
 from .sharded import ShardedSearch, init_nccl_comm, partition_pages
-from .topk import retrieval_metrics, topk as top_k, topk_merge
+from .topk import retrieval_metrics, topk as top_k, topk_merge, topk_metrics
 
 __version__ = "0.1.0"
 SUBMODULES = ("_lib", "corpus", "normalize", "retrieval", "sharded", "synth", "topk")

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "evdr_topk": ([_vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp], _i),
     "evdr_topk_merge": ([_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
     "evdr_retrieval_metrics": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
+    "evdr_topk_metrics": ([_vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp], _i),
     "evdr_comm_unique_id": ([_vp], _i),
     "evdr_comm_init": ([_vp, _vp, _i, _i], _i),
     "evdr_comm_world": ([_vp], _i),

@@ -56,6 +56,70 @@ __device__ __forceinline__ void warp_insert(const WarpList& L, int k, int lane, 
   __syncwarp();
 }
 
+// trec_eval-style measures of ONE query from its ranked ids; double accumulators like trec_eval.
+// out[m][j][q], m: 0 ndcg, 1 map, 2 recall, 3 precision, 4 mrr
+struct MetricArgs {
+  const int32_t* qrel_off;
+  const long long* qrel_ids;
+  const int32_t* qrel_rels;
+  const int32_t* k_values;
+  int nk;
+  double* out;      // nullptr: no measures
+};
+
+__device__ void query_metrics(const long long* __restrict__ ids, int kmax, int q, int nq,
+                              const MetricArgs& ma) {
+  const int b = ma.qrel_off[q], e = ma.qrel_off[q + 1];
+  int n_rel = 0;
+  for (int i = b; i < e; ++i) n_rel += ma.qrel_rels[i] > 0;
+  for (int j = 0; j < ma.nk; ++j) {
+    const int k = ma.k_values[j];
+    const int kk = min(k, kmax);
+    double dcg = 0.0, ap = 0.0, rr = 0.0;
+    int hits = 0;
+    for (int i = 0; i < kk; ++i) {
+      long long id = ids[i];
+      int rel = 0;
+      if (id >= 0)
+        for (int t = b; t < e; ++t)
+          if (ma.qrel_ids[t] == id) { rel = ma.qrel_rels[t]; break; }
+      if (rel > 0) {
+        dcg += (double)rel / log2((double)i + 2.0);
+        ++hits;
+        ap += (double)hits / (double)(i + 1);
+        if (rr == 0.0) rr = 1.0 / (double)(i + 1);
+      }
+    }
+    // ideal DCG: positive rels in descending order, cut at k (selection without storage)
+    double idcg = 0.0;
+    {
+      int last_rel = 0x7fffffff;  // rels emitted so far are >= last_rel
+      int emitted = 0;
+      while (emitted < k && emitted < n_rel) {
+        int best = 0, cnt = 0;
+        for (int t = b; t < e; ++t) {
+          int r = ma.qrel_rels[t];
+          if (r > 0 && r < last_rel) {
+            if (r > best) { best = r; cnt = 1; }
+            else if (r == best) ++cnt;
+          }
+        }
+        if (best == 0) break;
+        for (int c = 0; c < cnt && emitted < k; ++c, ++emitted)
+          idcg += (double)best / log2((double)emitted + 2.0);
+        last_rel = best;
+      }
+    }
+    const size_t o = (size_t)j * nq + q;
+    const size_t plane = (size_t)ma.nk * nq;
+    ma.out[0 * plane + o] = idcg > 0.0 ? dcg / idcg : 0.0;
+    ma.out[1 * plane + o] = n_rel > 0 ? ap / (double)n_rel : 0.0;
+    ma.out[2 * plane + o] = n_rel > 0 ? (double)hits / (double)n_rel : 0.0;
+    ma.out[3 * plane + o] = (double)hits / (double)k;
+    ma.out[4 * plane + o] = rr;
+  }
+}
+
 // grid (nsplit, nq).  Source is either implicit columns of a score row
 // (cand_ids == nullptr: id = col + id_offset, tie = tie_rank ? tie_rank[col] : col)
 // or explicit candidates (tie = cand_tie ? cand_tie[i] : cand_ids[i]).
@@ -64,7 +128,7 @@ topk_select_kernel(const float* __restrict__ scores, long long ld, int n,
                    const int32_t* __restrict__ tie_rank, long long id_offset,
                    const long long* __restrict__ cand_ids, const long long* __restrict__ cand_tie,
                    int k, float* __restrict__ out_s, long long* __restrict__ out_tie,
-                   long long* __restrict__ out_id) {
+                   long long* __restrict__ out_id, const MetricArgs ma) {
   extern __shared__ unsigned char smem_raw[];
   // layout: per warp k floats, k tie, k id
   float* ws = reinterpret_cast<float*>(smem_raw);
@@ -146,68 +210,18 @@ topk_select_kernel(const float* __restrict__ scores, long long ld, int n,
       oi[rank] = wi[w * TOPK_MAX + j];
     }
   }
+  // fused tail: the CTA that produced a query's final ranking also scores it (nDCG/MAP/Recall/P/MRR)
+  if (ma.out != nullptr) {
+    __syncthreads();
+    if (tid == 0) query_metrics(oi, k, q, gridDim.y, ma);
+  }
 }
 
-// trec_eval-style per-query measures; one thread per query, double accumulators.
-// out[m][j][q], m: 0 ndcg, 1 map, 2 recall, 3 precision, 4 mrr
 __global__ void __launch_bounds__(128)
-metrics_kernel(const long long* __restrict__ top_ids, int kmax, int nq,
-               const int32_t* __restrict__ qrel_off, const long long* __restrict__ qrel_ids,
-               const int32_t* __restrict__ qrel_rels, const int32_t* __restrict__ k_values, int nk,
-               double* __restrict__ out) {
+metrics_kernel(const long long* __restrict__ top_ids, int kmax, int nq, const MetricArgs ma) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
-  const int b = qrel_off[q], e = qrel_off[q + 1];
-  int n_rel = 0;
-  for (int i = b; i < e; ++i) n_rel += qrel_rels[i] > 0;
-  const long long* ids = top_ids + (size_t)q * kmax;
-  for (int j = 0; j < nk; ++j) {
-    const int k = k_values[j];
-    const int kk = min(k, kmax);
-    double dcg = 0.0, ap = 0.0, rr = 0.0;
-    int hits = 0;
-    for (int i = 0; i < kk; ++i) {
-      long long id = ids[i];
-      int rel = 0;
-      if (id >= 0)
-        for (int t = b; t < e; ++t)
-          if (qrel_ids[t] == id) { rel = qrel_rels[t]; break; }
-      if (rel > 0) {
-        dcg += (double)rel / log2((double)i + 2.0);
-        ++hits;
-        ap += (double)hits / (double)(i + 1);
-        if (rr == 0.0) rr = 1.0 / (double)(i + 1);
-      }
-    }
-    // ideal DCG: positive rels in descending order, cut at k (selection without storage)
-    double idcg = 0.0;
-    {
-      int last_rel = 0x7fffffff;  // rels emitted so far are >= last_rel
-      int emitted = 0;
-      while (emitted < k && emitted < n_rel) {
-        // next largest value strictly below last_rel, and how many have it
-        int best = 0, cnt = 0;
-        for (int t = b; t < e; ++t) {
-          int r = qrel_rels[t];
-          if (r > 0 && r < last_rel) {
-            if (r > best) { best = r; cnt = 1; }
-            else if (r == best) ++cnt;
-          }
-        }
-        if (best == 0) break;
-        for (int c = 0; c < cnt && emitted < k; ++c, ++emitted)
-          idcg += (double)best / log2((double)emitted + 2.0);
-        last_rel = best;
-      }
-    }
-    const size_t o = (size_t)j * nq + q;
-    const size_t plane = (size_t)nk * nq;
-    out[0 * plane + o] = idcg > 0.0 ? dcg / idcg : 0.0;
-    out[1 * plane + o] = n_rel > 0 ? ap / (double)n_rel : 0.0;
-    out[2 * plane + o] = n_rel > 0 ? (double)hits / (double)n_rel : 0.0;
-    out[3 * plane + o] = (double)hits / (double)k;
-    out[4 * plane + o] = rr;
-  }
+  query_metrics(top_ids + (size_t)q * kmax, kmax, q, nq, ma);
 }
 
 static int pick_nsplit(const evdr_handle* h, int nq, int n) {
@@ -224,13 +238,16 @@ static size_t topk_smem() {
 // two-stage selection shared by evdr_topk / evdr_topk_merge
 static int run_topk(evdr_handle* h, const float* scores, long long ld, int nq, int n,
                     const int32_t* tie_rank, long long id_offset, const long long* cand_ids,
-                    int k, float* top_s, long long* top_id, cudaStream_t st) {
+                    int k, float* top_s, long long* top_id, cudaStream_t st,
+                    const MetricArgs* metrics = nullptr) {
+  const MetricArgs none = {nullptr, nullptr, nullptr, nullptr, 0, nullptr};
+  const MetricArgs fin = metrics ? *metrics : none;
   const size_t smem = topk_smem();
   EVDR_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nsplit = pick_nsplit(h, nq, n);
   if (nsplit == 1) {
     topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
-        scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, top_s, nullptr, top_id);
+        scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, top_s, nullptr, top_id, fin);
     EVDR_LAUNCH_CHECK("topk_select_kernel");
     return EVDR_OK;
   }
@@ -241,10 +258,10 @@ static int run_topk(evdr_handle* h, const float* scores, long long ld, int nq, i
   long long* p_id = p_tie + per;
   float* p_s = reinterpret_cast<float*>(p_id + per);
   topk_select_kernel<<<dim3(nsplit, nq), TOPK_WARPS * 32, smem, st>>>(
-      scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, p_s, p_tie, p_id);
+      scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, p_s, p_tie, p_id, none);
   EVDR_LAUNCH_CHECK("topk_select_kernel(stage1)");
   topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
-      p_s, (long long)nsplit * k, nsplit * k, nullptr, 0, p_id, p_tie, k, top_s, nullptr, top_id);
+      p_s, (long long)nsplit * k, nsplit * k, nullptr, 0, p_id, p_tie, k, top_s, nullptr, top_id, fin);
   EVDR_LAUNCH_CHECK("topk_select_kernel(stage2)");
   EVDR_CUDA(cudaFreeAsync(ws, st));
   return EVDR_OK;
@@ -288,11 +305,26 @@ int evdr_retrieval_metrics(evdr_handle* h, const int64_t* top_ids, int kmax, int
   EVDR_CHECK_ARG(top_ids && qrel_off && qrel_ids && qrel_rels && k_values && out,
                  "evdr_retrieval_metrics: null pointer");
   EVDR_CHECK_ARG(kmax >= 1 && nq >= 1 && nk >= 1, "evdr_retrieval_metrics: bad shape");
+  const MetricArgs ma = {qrel_off, reinterpret_cast<const long long*>(qrel_ids), qrel_rels, k_values, nk, out};
   metrics_kernel<<<(nq + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(top_ids), kmax, nq, qrel_off,
-      reinterpret_cast<const long long*>(qrel_ids), qrel_rels, k_values, nk, out);
+      reinterpret_cast<const long long*>(top_ids), kmax, nq, ma);
   EVDR_LAUNCH_CHECK("metrics_kernel");
   return EVDR_OK;
+}
+
+int evdr_topk_metrics(evdr_handle* h, const float* scores, int64_t ld, int nq, int np, int kmax,
+                      const int32_t* tie_rank, int64_t id_offset, const int32_t* qrel_off,
+                      const int64_t* qrel_ids, const int32_t* qrel_rels, const int32_t* k_values,
+                      int nk, float* top_scores, int64_t* top_ids, double* out, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(scores && top_scores && top_ids && qrel_off && qrel_ids && qrel_rels && k_values && out,
+                 "evdr_topk_metrics: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && ld >= np && nk >= 1, "evdr_topk_metrics: bad shape");
+  EVDR_CHECK_ARG(kmax >= 1 && kmax <= TOPK_MAX, "evdr_topk_metrics: kmax=%d outside [1,%d]", kmax, TOPK_MAX);
+  EVDR_CHECK_ARG(nq <= 65535, "evdr_topk_metrics: nq=%d > 65535 per call", nq);
+  const MetricArgs ma = {qrel_off, reinterpret_cast<const long long*>(qrel_ids), qrel_rels, k_values, nk, out};
+  return run_topk(h, scores, ld, nq, np, tie_rank, id_offset, nullptr, kmax, top_scores,
+                  reinterpret_cast<long long*>(top_ids), static_cast<cudaStream_t>(stream), &ma);
 }
 
 }  // extern "C"

@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from ._lib import TC_DIM, TC_LQ
 from .corpus import PackedPages, _float_operand, _mask_u8, pack_queries
-from .topk import retrieval_metrics, topk
+from .topk import retrieval_metrics, topk, topk_metrics
 
 __all__ = [
     "score_multi_vector_masked", "BaseVisualRetrieverProcessor", "CustomRetrievalEvaluator",
@@ -309,8 +309,7 @@ class CustomRetrievalEvaluator:
         kmax = min(max(self.k_values), _lib.TOPK_MAX)
         if max(self.k_values) > _lib.TOPK_MAX:
             raise NotImplementedError(f"k_values above {_lib.TOPK_MAX} are not supported")
-        _, ids = topk(scores, kmax, tie_rank=tie_rank)
-        m = retrieval_metrics(ids, qrel_off, qrel_ids, qrel_rels, self.k_values)
+        _, ids, m = topk_metrics(scores, kmax, qrel_off, qrel_ids, qrel_rels, self.k_values, tie_rank=tie_rank)
         if tie_rank is not None:  # mteb's MRR sorts stably: ties in column order
             _, ids2 = topk(scores, kmax, tie_rank=None)
             m[4] = retrieval_metrics(ids2, qrel_off, qrel_ids, qrel_rels, self.k_values)[4]

@@ -83,3 +83,39 @@ def retrieval_metrics(top_ids: torch.Tensor, qrel_off: torch.Tensor, qrel_ids: t
                                           len(k_values), out.data_ptr(), _lib.stream_ptr(dev)),
                "evdr_retrieval_metrics")
     return out
+
+
+def topk_metrics(scores: torch.Tensor, kmax: int, qrel_off: torch.Tensor, qrel_ids: torch.Tensor,
+                 qrel_rels: torch.Tensor, k_values: Sequence[int], tie_rank: torch.Tensor | None = None,
+                 id_offset: int = 0):
+    """Fused top-kmax + measures (evdr_topk_metrics): returns (top_scores, top_ids, metrics (5, nk, nq))."""
+    _lib.require_cuda(scores, "scores")
+    if scores.dtype != torch.float32 or scores.dim() != 2:
+        raise ValueError("scores must be a 2-D float32 tensor")
+    if scores.stride(1) != 1:
+        scores = scores.contiguous()
+    nq, npg = scores.shape
+    if not (1 <= kmax <= TOPK_MAX):
+        raise ValueError(f"kmax={kmax} outside [1,{TOPK_MAX}]")
+    if nq > 65535:
+        raise NotImplementedError("more than 65535 queries per call")
+    dev = scores.device
+    if tie_rank is not None:
+        tie_rank = tie_rank.to(device=dev, dtype=torch.int32).contiguous()
+    qrel_off = qrel_off.to(device=dev, dtype=torch.int32).contiguous()
+    qrel_ids = qrel_ids.to(device=dev, dtype=torch.int64).contiguous()
+    qrel_rels = qrel_rels.to(device=dev, dtype=torch.int32).contiguous()
+    if qrel_ids.numel() == 0:
+        qrel_ids = torch.zeros(1, dtype=torch.int64, device=dev)
+        qrel_rels = torch.zeros(1, dtype=torch.int32, device=dev)
+    kv = torch.tensor(list(k_values), dtype=torch.int32, device=dev)
+    top_s = torch.empty((nq, kmax), dtype=torch.float32, device=dev)
+    top_i = torch.empty((nq, kmax), dtype=torch.int64, device=dev)
+    out = torch.empty((5, len(k_values), nq), dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.evdr_topk_metrics(_lib.handle(dev), scores.data_ptr(), scores.stride(0), nq, npg, kmax,
+                                     _lib.ptr(tie_rank), id_offset, qrel_off.data_ptr(), qrel_ids.data_ptr(),
+                                     qrel_rels.data_ptr(), kv.data_ptr(), len(k_values), top_s.data_ptr(),
+                                     top_i.data_ptr(), out.data_ptr(), _lib.stream_ptr(dev)),
+               "evdr_topk_metrics")
+    return top_s, top_i, out

@@ -177,6 +177,15 @@ EVDR_API int evdr_retrieval_metrics(evdr_handle* h, const int64_t* top_ids_dev, 
                                     const int32_t* k_values_dev, int nk,
                                     double* out_dev, void* stream);
 
+/* Fused form: top-kmax selection and the measures in ONE pass -- the CTA that produces a query's
+ * final ranking also scores it (qrel ids are column + id_offset). */
+EVDR_API int evdr_topk_metrics(evdr_handle* h, const float* scores_dev, int64_t ld, int nq, int np,
+                               int kmax, const int32_t* tie_rank_dev, int64_t id_offset,
+                               const int32_t* qrel_off_dev, const int64_t* qrel_ids_dev,
+                               const int32_t* qrel_rels_dev, const int32_t* k_values_dev, int nk,
+                               float* top_scores_dev, int64_t* top_ids_dev, double* out_dev,
+                               void* stream);
+
 /* ------------------------------------------------------------------------
  * Multi-GPU: pages sharded by contiguous range, queries replicated.  Each rank
  * runs its local scan + evdr_topk, then one ncclAllGather of nq*k (score, id)

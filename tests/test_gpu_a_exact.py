@@ -267,3 +267,57 @@ def test_dropin_module_binds_by_reference_import_path(cuda):
         sys.path.remove(dropin)
         for k in [k for k in sys.modules if k == "evaluator" or k.startswith("evaluator.")]:
             del sys.modules[k]
+
+
+@pytest.mark.parametrize("nq,n", [(40, 300), (3, 150_000)])
+def test_fused_topk_metrics(evdr, cuda, nq, n):
+    """evdr_topk_metrics (one pass) == evdr_topk + evdr_retrieval_metrics == the trec oracle."""
+    g = torch.Generator().manual_seed(nq + n)
+    s = torch.randn(nq, n, generator=g).round(decimals=2)              # ties
+    off, ids, rels = [0], [], []
+    for q in range(nq):
+        for j in torch.randperm(n, generator=g)[: int(torch.randint(1, 5, (1,), generator=g))].tolist():
+            ids.append(j)
+            rels.append(int(torch.randint(0, 4, (1,), generator=g)))
+        off.append(len(ids))
+    off_t, ids_t, rels_t = torch.tensor(off), torch.tensor(ids), torch.tensor(rels)
+    ks = [1, 3, 5, 10, 50, 70, 100]
+    ts, ti, m = evdr.topk_metrics(s.to(cuda), 100, off_t, ids_t, rels_t, ks)
+    ts2, ti2 = evdr.top_k(s.to(cuda), 100)
+    m2 = evdr.retrieval_metrics(ti2, off_t, ids_t, rels_t, ks)
+    assert torch.equal(ti, ti2) and torch.equal(ts, ts2) and torch.equal(m, m2)
+    m = m.cpu().numpy()
+    for q in range(min(nq, 10)):
+        qrel = {f"{j:07d}": r for j, r in zip(ids[off[q]:off[q + 1]], rels[off[q]:off[q + 1]])}
+        ranking = [f"{j:07d}" for j in ti[q].tolist()]
+        want = to.per_query_measures(qrel, ranking, ks)
+        for jk, k in enumerate(ks):
+            assert m[0, jk, q] == pytest.approx(want[f"ndcg@{k}"], abs=1e-12)
+            assert m[1, jk, q] == pytest.approx(want[f"map@{k}"], abs=1e-12)
+            assert m[2, jk, q] == pytest.approx(want[f"recall@{k}"], abs=1e-12)
+            assert m[3, jk, q] == pytest.approx(want[f"p@{k}"], abs=1e-12)
+
+
+def test_evaluate_scores_fast_path(evdr, cuda):
+    """Device-resident evaluation (no dicts): same numbers as the dict signature."""
+    qrels, results = _random_eval_problem(5, nq=30, nd=120, ties=True)
+    qids = [q for q in results]
+    docs = list(results[qids[0]].keys())
+    dense = torch.tensor([[results[q][d] for d in docs] for q in qids], dtype=torch.float32)
+    order = sorted(docs, reverse=True)
+    tie = torch.empty(len(docs), dtype=torch.int32)
+    tie[torch.tensor([docs.index(d) for d in order])] = torch.arange(len(docs), dtype=torch.int32)
+    off, ids, rels, extra = [0], [], [], len(docs)
+    for q in qids:
+        for d, r in qrels[q].items():
+            if d in docs:
+                ids.append(docs.index(d))
+            else:
+                ids.append(extra)
+                extra += 1
+            rels.append(r)
+        off.append(len(ids))
+    ev = evdr.CustomRetrievalEvaluator()
+    got = ev.evaluate_scores(dense.to(cuda), torch.tensor(off), torch.tensor(ids), torch.tensor(rels), tie_rank=tie.to(cuda))
+    want = ev.compute_mteb_metrics(qrels, results)
+    assert got == want
