@@ -56,6 +56,16 @@ METRIC = "maxsim_query_page_pairs_per_sec"
 UNIT = "pairs/s"
 
 
+def measured_traffic(nq: int, pages: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very
+    configuration (profiles/traffic.json); None for configurations that were not captured."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text()).get(f"{nq}x{pages}", {}).get("bytes")
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -305,7 +315,8 @@ def main():
                 "frac": achieved / peaks["bf16_tflops_sustained"],
                 "peak_kind": f"{peaks['source']} sustained cuBLAS bf16 (each launch runs {ms_kernel:.0f} ms, power-capped regime)",
                 "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "burst_peak": peaks["bf16_tflops"],
-                "ms_per_launch": ms_kernel, "algorithmic_flops_per_launch": flops, "traffic": None}
+                "ms_per_launch": ms_kernel, "algorithmic_flops_per_launch": flops,
+                "algorithmic_bytes_per_launch": npg * BYTES_PER_PAGE, "traffic": measured_traffic(nq, npg)}
 
     extras = {}
     if not args.no_extras:
@@ -355,11 +366,13 @@ def side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus
         if nq == 1:
             gbs = pages_s * BYTES_PER_PAGE / 1e9
             rec["roofline"] = {"kernel": "maxsim_tc_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": measured_traffic(nq, npg),
+                               "algorithmic_bytes_per_launch": npg * BYTES_PER_PAGE}
         else:
             tf = nq * npg * FLOPS_PER_PAIR / (ms_scan * 1e-3) / 1e12
             rec["roofline"] = {"kernel": "maxsim_tc_kernel", "bound": "tensor", "achieved": tf,
-                               "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"]}
+                               "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
+                               "traffic": measured_traffic(nq, npg)}
         out[f"q{nq}"] = rec
     return out
 

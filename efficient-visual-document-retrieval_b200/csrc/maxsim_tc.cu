@@ -49,6 +49,7 @@ struct TcParams {
   int n_pblocks, n_qgroups;
   int g_base, g_rem;          // query tiles per group: g_base (+1 for the first g_rem groups)
   int stream_hint;            // 1: page tiles are read once (evict-first)
+  int* sched;                 // dynamic scheduler: global item counter (zeroed per launch); CG2: unused
 };
 
 template <int R, int BN, int STAGES, bool CG2>
@@ -59,8 +60,10 @@ struct TcCfg {
   static constexpr int A_BYTES = R * A_TILE_BYTES;
   static constexpr int B_BYTES = STAGES * B_STAGE_BYTES;
   static constexpr int BAR_OFF = A_BYTES + B_BYTES;
-  // barriers: full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2], tmem ptr
-  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 6) + 8;
+  // barriers: full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2], tmem ptr,
+  // then the scheduler ring: slot_full[NSLOT], slot_empty[NSLOT], item[NSLOT]
+  static constexpr int NSLOT = 4;
+  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 6) + 8 + 8 * 2 * NSLOT + 4 * NSLOT;
   static constexpr int TOTAL = BAR_OFF + BAR_BYTES + 1024;  // + alignment slack
   static constexpr int TILES_PER_GROUP = CG2 ? 2 * R : R;
 };
@@ -89,6 +92,12 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   auto bar_t_full = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
   auto bar_t_empty = [&](int b) { return bars + 8u * (2 * STAGES + 4 + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 6);
+  constexpr int NSLOT = S::NSLOT;
+  const uint32_t sched_base = tmem_slot + 8u;
+  auto bar_s_full = [&](int s) { return sched_base + 8u * s; };
+  auto bar_s_empty = [&](int s) { return sched_base + 8u * (NSLOT + s); };
+  volatile int* item_ring =
+      reinterpret_cast<volatile int*>(smem_raw + (sched_base + 8u * 2 * NSLOT - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -106,6 +115,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     mbar_init(bar_a_empty, 1);
     // tmem_empty lives in the leader: 4 epilogue warps of each CTA of the pair arrive on it
     for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full(b), 1); mbar_init(bar_t_empty(b), CG2 ? 8 : 4); }
+    // scheduler ring: the producer publishes item indices, the MMA thread + 4 epilogue warps consume
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), 5); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -132,7 +143,24 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       const uint64_t pol = prm.stream_hint ? policy_evict_first() : policy_evict_last();
       int stage = 0, phase = 0, a_loads = 0, cur_g = -1;
       const uint32_t a_full_tx = CG2 ? mapa_u32(bar_a_full, 0) : bar_a_full;
-      for (int it = unit; it < n_items; it += n_units) {
+      // dynamic tile scheduler (single-CTA flavour): the producer draws the next item from a global
+      // counter and publishes it to the other roles through a small shared-memory ring, so all CTAs
+      // work on neighbouring items at any time and re-reads of a page block hit L2 however long the
+      // run is.  The pair flavour keeps the static round-robin deal.
+      int sslot = 0, sphase = 0;
+      auto next_item = [&](int cur) -> int {
+        if constexpr (CG2) {
+          return cur < 0 ? unit : cur + n_units;
+        } else {
+          mbar_wait(bar_s_empty(sslot), sphase ^ 1);
+          const int v = atomicAdd(prm.sched, 1);
+          item_ring[sslot] = v;
+          mbar_arrive(bar_s_full(sslot));
+          if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
+          return v;
+        }
+      };
+      for (int it = next_item(-1); it < n_items; it = next_item(it)) {
         const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
         const int p0 = pb * prm.ppi, p1 = min(p0 + prm.ppi, prm.np);
         const int c0 = prm.chunk_off[p0], c1 = prm.chunk_off[p1];
@@ -180,7 +208,19 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       auto commit = [&](uint32_t bar) {
         if constexpr (CG2) mma_commit_cg2_mc(bar, (uint16_t)0x3); else mma_commit(bar);
       };
-      for (int it = unit; it < n_items; it += n_units) {
+      int sslot = 0, sphase = 0;
+      auto next_item = [&](int cur) -> int {
+        if constexpr (CG2) {
+          return cur < 0 ? unit : cur + n_units;
+        } else {
+          mbar_wait(bar_s_full(sslot), sphase);
+          const int v = item_ring[sslot];
+          mbar_arrive(bar_s_empty(sslot));
+          if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
+          return v;
+        }
+      };
+      for (int it = next_item(-1); it < n_items; it = next_item(it)) {
         const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
         const int p0 = pb * prm.ppi, p1 = min(p0 + prm.ppi, prm.np);
         const int c0 = prm.chunk_off[p0], c1 = prm.chunk_off[p1];
@@ -239,7 +279,20 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       }
     };
 
-    for (int it = unit; it < n_items; it += n_units) {
+    int sslot = 0, sphase = 0;
+    auto next_item = [&](int cur) -> int {
+      if constexpr (CG2) {
+        return cur < 0 ? unit : cur + n_units;
+      } else {
+        mbar_wait(bar_s_full(sslot), sphase);
+        const int v = item_ring[sslot];
+        __syncwarp();                                  // every lane has read the slot
+        if (lane == 0) mbar_arrive(bar_s_empty(sslot));
+        if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
+        return v;
+      }
+    };
+    for (int it = next_item(-1); it < n_items; it = next_item(it)) {
       const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
       const int p0 = pb * prm.ppi, p1 = min(p0 + prm.ppi, prm.np);
       const int c0 = prm.chunk_off[p0], c1 = prm.chunk_off[p1];
@@ -409,7 +462,15 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
-  EVDR_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmP, prm));
+  prm.sched = nullptr;
+  if (!CG2) {  // stream-ordered 4-byte item counter, zeroed for this launch
+    EVDR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prm.sched), sizeof(int), st));
+    EVDR_CUDA(cudaMemsetAsync(prm.sched, 0, sizeof(int), st));
+  }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmQ, tmP, prm);
+  if (prm.sched) cudaFreeAsync(prm.sched, st);
+  if (le != cudaSuccess)
+    return set_error(EVDR_ERR_CUDA, "launch of maxsim_tc_kernel failed: %s", cudaGetErrorString(le));
   return EVDR_OK;
 }
 
@@ -454,11 +515,18 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
   if (ppi <= 0) { const char* e = getenv("EVDR_TC_PPI"); if (e) ppi = atoi(e); }
   if (ppi <= 0) {
     // ~64K tokens per item (amortises the query-tile reload between items), tile-aligned for
-    // uniform pages; shrink while there are too few items to balance the grid
+    // uniform pages ...
     const double avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
     ppi = (int)(65536.0 / avg_tok + 0.5);
     if (ppi < 1) ppi = 1;
+    // ... but the `units` items in flight span units / n_qgroups page blocks, which must stay
+    // L2-resident (126 MB) for the other query groups' re-reads to hit: cap the window at ~48 MB
+    if (n_qgroups > 1) {
+      const double cap = 48e6 * n_qgroups / ((double)units * avg_tok * EVDR_TC_DIM * 2);
+      if (ppi > cap) ppi = cap < 8.0 ? 8 : (int)cap;   // >= 8 pages: keep the query-tile reload amortised
+    }
     if (ppi >= 16) ppi = (ppi / 16) * 16;
+    // ... and there must be enough items to balance the grid
     while (ppi > 1 && (long long)((np + ppi - 1) / ppi) * n_qgroups < 16LL * units) ppi = (ppi + 1) / 2;
   }
   if (ppi > np) ppi = np;
