@@ -33,18 +33,19 @@ def _float_operand(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
-def pack_queries(Q: torch.Tensor, qmask: torch.Tensor):
-    """(nq, lq<=32, 128) -> bf16 (nq, 32, 128) with masked slots zeroed, uint8 (nq, 32)."""
+def pack_queries(Q: torch.Tensor, qmask: torch.Tensor, k_blocks: int = 1):
+    """(nq, lq<=32, 128) -> bf16 (nq, 32, 128*k_blocks) with masked slots zeroed, uint8 (nq, 32).
+    k_blocks=3 writes the [hi | hi | lo] rows of the bf16x3 split."""
     _lib.require_cuda(Q, "Q")
     nq, lq, d = Q.shape
     Qc = _float_operand(Q)
     qm = _mask_u8(qmask)
     dev = Q.device
-    Qb = torch.empty((nq, TC_LQ, TC_DIM), dtype=torch.bfloat16, device=dev)
+    Qb = torch.empty((nq, TC_LQ, TC_DIM * k_blocks), dtype=torch.bfloat16, device=dev)
     qm32 = torch.empty((nq, TC_LQ), dtype=torch.uint8, device=dev)
     lib = _lib.load()
     _lib.check(lib.evdr_pack_queries(_lib.handle(dev), Qc.data_ptr(), _lib.dtype_code(Qc), qm.data_ptr(),
-                                     nq, lq, d, Qb.data_ptr(), qm32.data_ptr(), _lib.stream_ptr(dev)),
+                                     nq, lq, d, k_blocks, Qb.data_ptr(), qm32.data_ptr(), _lib.stream_ptr(dev)),
                "evdr_pack_queries")
     return Qb, qm32
 
@@ -53,8 +54,9 @@ class PackedPages:
     """Device-resident packed corpus shard."""
 
     def __init__(self, tokens: torch.Tensor, chunk_off: torch.Tensor, n_pages: int, total_chunks: int,
-                 page_offset: int = 0):
-        self.tokens = tokens            # bf16 [n_tokens, 128]
+                 page_offset: int = 0, k_blocks: int = 1):
+        self.k_blocks = int(k_blocks)   # 1 = bf16 rows, 3 = bf16x3 split rows [hi | lo | hi]
+        self.tokens = tokens            # bf16 [n_tokens, 128 * k_blocks]
         self.chunk_off = chunk_off      # int32 [n_pages + 1]
         self.n_pages = int(n_pages)
         self.total_chunks = int(total_chunks)
@@ -64,13 +66,14 @@ class PackedPages:
     # ------------------------------------------------------------------ builders
     @staticmethod
     def from_padded(P: torch.Tensor, pmask: torch.Tensor, *, normalize: bool = False,
-                    varlen: bool = False, page_offset: int = 0) -> "PackedPages":
+                    varlen: bool = False, page_offset: int = 0, k_blocks: int = 1) -> "PackedPages":
         """Pack the reference's padded layout: P (np, lp, 128) fp32|bf16, pmask (np, lp) any dtype.
 
         varlen=False sizes every page at ceil(lp/16) chunks (no host sync; right for the per-step
         student tensor).  varlen=True trims each page after its last valid token (one device->host
         read of the total; right for a corpus that is packed once).
         normalize=True fuses l2_normalize(P * pmask[..., None]) (mainv2_iter_listwise.py:280).
+        k_blocks=3 stores the bf16x3 split (3x the bytes, near-fp32 similarities).
         """
         _lib.require_cuda(P, "P")
         npg, lp, d = P.shape
@@ -89,11 +92,11 @@ class PackedPages:
             total = int(chunk_off[-1].item())
         else:
             total = npg * ((lp + CHUNK - 1) // CHUNK)
-        tokens = torch.empty((total * CHUNK, TC_DIM), dtype=torch.bfloat16, device=dev)
+        tokens = torch.empty((total * CHUNK, TC_DIM * k_blocks), dtype=torch.bfloat16, device=dev)
         _lib.check(lib.evdr_pack_pages(h, Pc.data_ptr(), _lib.dtype_code(Pc), pm.data_ptr(),
-                                       chunk_off.data_ptr(), npg, lp, d, 1 if normalize else 0,
+                                       chunk_off.data_ptr(), npg, lp, d, 1 if normalize else 0, k_blocks,
                                        tokens.data_ptr(), st), "evdr_pack_pages")
-        return PackedPages(tokens, chunk_off, npg, total, page_offset)
+        return PackedPages(tokens, chunk_off, npg, total, page_offset, k_blocks)
 
     @staticmethod
     def from_uniform_tokens(tokens: torch.Tensor, page_offset: int = 0) -> "PackedPages":
@@ -118,12 +121,12 @@ class PackedPages:
         _lib.check(lib.evdr_maxsim_packed_fwd(
             _lib.handle(dev), Qb.data_ptr(), qm32.data_ptr(), nq, self.tokens.data_ptr(),
             self.tokens.shape[0], self.chunk_off.data_ptr(), self.n_pages, self.total_chunks,
-            pages_per_item, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)),
+            pages_per_item, self.k_blocks, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)),
             "evdr_maxsim_packed_fwd")
         return out
 
     def score(self, Q: torch.Tensor, qmask: torch.Tensor) -> torch.Tensor:
-        Qb, qm32 = pack_queries(Q, qmask)
+        Qb, qm32 = pack_queries(Q, qmask, self.k_blocks)
         return self.score_packed(Qb, qm32)
 
     def search(self, Q: torch.Tensor, qmask: torch.Tensor, k: int = 10):

@@ -14,6 +14,7 @@
 #include "../../include/evdr.h"
 
 #define EVDR_VERSION_INT 100  // 0.1.0
+#define EVDR_SCHED_RING 4096
 
 // ---------------------------------------------------------------------------
 // error plumbing: thread-local message + status code, no exceptions
@@ -60,6 +61,10 @@ struct evdr_handle {
   int cc_major, cc_minor;
   size_t smem_optin;
   evdr_encode_tiled_fn encode_tiled;
+  // scheduler counters of the tensor-core kernel: a ring of device ints owned by the handle (one per
+  // launch, zeroed on the launch stream), so the hot path never allocates
+  int* sched_ring;
+  unsigned sched_next;
   // multi-GPU
   void* nccl_comm;  // ncclComm_t
   int rank, world;

@@ -59,6 +59,19 @@ int evdr_create(int device, evdr_handle** out) {
     return evdr::set_error(EVDR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   h->encode_tiled = reinterpret_cast<evdr_encode_tiled_fn>(fn);
+  if (cudaMalloc(reinterpret_cast<void**>(&h->sched_ring), sizeof(int) * EVDR_SCHED_RING) != cudaSuccess) {
+    delete h;
+    return evdr::set_error(EVDR_ERR_CUDA, "cudaMalloc of the scheduler ring failed");
+  }
+  h->sched_next = 0;
+  // Stream-ordered scratch (cudaMallocAsync) is used for small temporaries.  By default the pool
+  // gives its memory back to the driver at every synchronisation, which turns each later
+  // allocation into a millisecond-scale driver call: keep the pool's memory cached instead.
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   *out = h;
   return EVDR_OK;
 }

@@ -166,8 +166,11 @@ bwd_dp_kernel(const float* __restrict__ gout, const TQ* __restrict__ Q,
     for (int i = tid; i < lp * d; i += blockDim.x) dPc[i] = 0.f;
     return;
   }
+  // a masked winner (possible only when every valid similarity is below the -1e4 fill) gets no
+  // gradient: the reference's masked_fill blocks it
+  const uint8_t* mc = pmask + (size_t)c * lp;
   for (int r = tid; r < R; r += blockDim.x)
-    if (qmask[r]) atomicAdd(&cnt[am[r]], 1);
+    if (qmask[r] && mc[am[r]]) atomicAdd(&cnt[am[r]], 1);
   __syncthreads();
   if (warp == 0) {  // exclusive scan over lp counters
     int carry = 0;
@@ -191,6 +194,7 @@ bwd_dp_kernel(const float* __restrict__ gout, const TQ* __restrict__ Q,
     for (int r0 = 0; r0 < R; r0 += 32) {
       int r = r0 + lane;
       bool act = (r < R) && qmask[r];
+      if (act) act = mc[am[r]] != 0;
       int m = act ? am[r] : -1 - lane;  // inactive lanes get unique keys
       unsigned peers = __match_any_sync(0xffffffffu, m);
       if (act) {
@@ -227,7 +231,8 @@ bwd_dp_kernel(const float* __restrict__ gout, const TQ* __restrict__ Q,
 template <typename TP>
 __global__ void __launch_bounds__(256)
 bwd_dq_kernel(const float* __restrict__ gout, const TP* __restrict__ P,
-              const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ has_page,
+              const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ pmask,
+              const uint8_t* __restrict__ has_page,
               const int32_t* __restrict__ argmax, int nq, int np, int lq, int lp, int d,
               float* __restrict__ dQ) {
   const int lane = threadIdx.x & 31;
@@ -243,6 +248,7 @@ bwd_dq_kernel(const float* __restrict__ gout, const TP* __restrict__ P,
         if (!has_page[c]) continue;
         float w = gout[(size_t)q * np + c];
         int m = argmax[(size_t)c * R + r];
+        if (!pmask[(size_t)c * lp + m]) continue;
         float4 pv = load4(P + ((size_t)c * lp + m) * d + d0);
         acc.x = fmaf(w, pv.x, acc.x);
         acc.y = fmaf(w, pv.y, acc.y);
@@ -252,6 +258,61 @@ bwd_dq_kernel(const float* __restrict__ gout, const TP* __restrict__ P,
     }
     *reinterpret_cast<float4*>(dQ + (size_t)r * d + d0) = acc;
   }
+}
+
+// Rescoring of tensor-core winners: one warp per (query-token row, page).  `am` holds the packed
+// slot chosen by the bf16 tcgen05 search (evdr_maxsim_packed_argmax); a slot that is a filler
+// (masked or beyond lp) is mapped back to the valid token it duplicates (nearest preceding valid
+// token, else the first valid one -- the pack rule), the token index replaces the slot in `am`
+// (the backward scatters through it) and the exact fp32 dot product goes to rowmax[c*R + r].
+template <typename TQ, typename TP>
+__global__ void __launch_bounds__(256)
+rescore_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P, const uint8_t* __restrict__ pmask,
+               int32_t* __restrict__ am, int R, int lp, int d, float* __restrict__ rowmax) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int c = blockIdx.y;
+  if (r >= R) return;
+  const uint8_t* mc = pmask + (size_t)c * lp;
+  int t = am[(size_t)c * R + r];
+  if (t < 0) t = 0;
+  if (t >= lp) t = lp - 1;
+  if (!mc[t]) {
+    int u = t;
+    while (u >= 0 && !mc[u]) --u;
+    if (u < 0) { u = 0; while (u < lp && !mc[u]) ++u; }
+    t = u;                                   // == lp: page without valid tokens
+  }
+  float v = kNegFill;                        // what the reference's masked_fill leaves (:198)
+  if (t < lp) {
+    const TQ* q = Q + (size_t)r * d;
+    const TP* p = P + ((size_t)c * lp + t) * d;
+    float acc = 0.f;
+    for (int i = lane * 4; i < d; i += 128) {
+      const float4 a = load4(q + i), b = load4(p + i);
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+    }
+    v = warp_sum(acc);
+  } else {
+    t = 0;
+  }
+  if (lane == 0) {
+    am[(size_t)c * R + r] = t;
+    rowmax[(size_t)c * R + r] = v;
+  }
+}
+
+template <typename TQ, typename TP>
+static int launch_rescore(const void* Q, const void* P, const uint8_t* pmask, int32_t* am, int R, int np,
+                          int lp, int d, float* rowmax, cudaStream_t st) {
+  dim3 grid((R + 7) / 8, np);
+  rescore_kernel<TQ, TP><<<grid, 256, 0, st>>>(static_cast<const TQ*>(Q), static_cast<const TP*>(P), pmask,
+                                                am, R, lp, d, rowmax);
+  EVDR_LAUNCH_CHECK("rescore_kernel");
+  return EVDR_OK;
 }
 
 __global__ void has_page_kernel(const uint8_t* __restrict__ pmask, int np, int lp,
@@ -308,6 +369,32 @@ int evdr_maxsim_fwd(evdr_handle* h, const void* Q, int q_dtype, const void* P, i
   return EVDR_OK;
 }
 
+int evdr_maxsim_rescore(evdr_handle* h, const void* Q, int q_dtype, const void* P, int p_dtype,
+                        const uint8_t* qmask, const uint8_t* pmask, int32_t* argmax, int nq, int np,
+                        int lq, int lp, int d, float* rowmax_ws, float* out, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(Q && P && qmask && pmask && argmax && rowmax_ws && out, "evdr_maxsim_rescore: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && lq >= 1 && lp >= 1 && d >= 4 && d % 4 == 0, "evdr_maxsim_rescore: bad shape");
+  EVDR_CHECK_ARG(np <= 65535, "evdr_maxsim_rescore: np=%d > 65535 pages per call (chunk the page axis)", np);
+  EVDR_CHECK_ARG((q_dtype == EVDR_F32 || q_dtype == EVDR_BF16) && (p_dtype == EVDR_F32 || p_dtype == EVDR_BF16),
+                 "evdr_maxsim_rescore: dtype must be EVDR_F32 or EVDR_BF16");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int R = nq * lq;
+  int rc;
+  if (q_dtype == EVDR_F32 && p_dtype == EVDR_F32)
+    rc = launch_rescore<float, float>(Q, P, pmask, argmax, R, np, lp, d, rowmax_ws, st);
+  else if (q_dtype == EVDR_F32)
+    rc = launch_rescore<float, __nv_bfloat16>(Q, P, pmask, argmax, R, np, lp, d, rowmax_ws, st);
+  else if (p_dtype == EVDR_F32)
+    rc = launch_rescore<__nv_bfloat16, float>(Q, P, pmask, argmax, R, np, lp, d, rowmax_ws, st);
+  else
+    rc = launch_rescore<__nv_bfloat16, __nv_bfloat16>(Q, P, pmask, argmax, R, np, lp, d, rowmax_ws, st);
+  if (rc != EVDR_OK) return rc;
+  rowsum_kernel<<<(np + 7) / 8, 256, 0, st>>>(rowmax_ws, qmask, pmask, nq, np, lq, lp, out);
+  EVDR_LAUNCH_CHECK("rowsum_kernel");
+  return EVDR_OK;
+}
+
 int evdr_maxsim_bwd(evdr_handle* h, const float* gout, const void* Q, int q_dtype, const void* P,
                     int p_dtype, const uint8_t* qmask, const uint8_t* pmask, const int32_t* argmax,
                     int nq, int np, int lq, int lp, int d, float* dP, float* dQ, void* stream) {
@@ -341,11 +428,11 @@ int evdr_maxsim_bwd(evdr_handle* h, const float* gout, const void* Q, int q_dtyp
     has_page_kernel<<<(np + 7) / 8, 256, 0, st>>>(pmask, np, lp, has);
     EVDR_LAUNCH_CHECK("has_page_kernel");
     if (p_dtype == EVDR_F32)
-      bwd_dq_kernel<float><<<(R + 7) / 8, 256, 0, st>>>(gout, static_cast<const float*>(P), qmask, has,
+      bwd_dq_kernel<float><<<(R + 7) / 8, 256, 0, st>>>(gout, static_cast<const float*>(P), qmask, pmask, has,
                                                         argmax, nq, np, lq, lp, d, dQ);
     else
       bwd_dq_kernel<__nv_bfloat16><<<(R + 7) / 8, 256, 0, st>>>(
-          gout, static_cast<const __nv_bfloat16*>(P), qmask, has, argmax, nq, np, lq, lp, d, dQ);
+          gout, static_cast<const __nv_bfloat16*>(P), qmask, pmask, has, argmax, nq, np, lq, lp, d, dQ);
     EVDR_LAUNCH_CHECK("bwd_dq_kernel");
     EVDR_CUDA(cudaFreeAsync(has, st));
   }

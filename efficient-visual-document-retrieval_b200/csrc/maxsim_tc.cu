@@ -35,8 +35,7 @@ namespace evdr {
 using namespace ptx;
 
 constexpr int TC_THREADS = 192;
-constexpr int A_TILE_BYTES = 128 * 128 * 2;      // 128 query-token rows x 128 dims bf16
-constexpr int A_HALF_BYTES = 128 * 64 * 2;       // one 64-wide K half (128-B rows)
+constexpr int A_HALF_BYTES = 128 * 64 * 2;       // one 64-wide K sub-tile (128 rows of 128 B)
 
 struct TcParams {
   const uint8_t* qmask32;     // [nq, 32]
@@ -49,14 +48,21 @@ struct TcParams {
   int n_pblocks, n_qgroups;
   int g_base, g_rem;          // query tiles per group: g_base (+1 for the first g_rem groups)
   int stream_hint;            // 1: page tiles are read once (evict-first)
+  int32_t* argmax;            // AM variant: [np, nq*lq] winning packed slot per (page, query token)
+  int lq;                     // AM variant: real query length (rows >= lq are padding)
   int* sched;                 // dynamic scheduler: global item counter (zeroed per launch); CG2: unused
 };
 
-template <int R, int BN, int STAGES, bool CG2>
+// KB = number of 128-wide K blocks of the operands: 1 = plain bf16; 3 = the bf16x3 split
+// A = [Qhi | Qhi | Qlo], B = [Phi | Plo | Phi] whose K = 384 contraction is Qhi.Phi + Qhi.Plo + Qlo.Phi,
+// i.e. the fp32 dot product up to the dropped Qlo.Plo term (~2^-18 relative) -- the high-fidelity mode
+template <int R, int BN, int STAGES, bool CG2, int KB = 1>
 struct TcCfg {
   static constexpr int B_ROWS = CG2 ? BN / 2 : BN;          // page tokens held by this CTA per stage
-  static constexpr int B_HALF_BYTES = B_ROWS * 64 * 2;       // one 64-wide K half
-  static constexpr int B_STAGE_BYTES = 2 * B_HALF_BYTES;
+  static constexpr int KSUB = 2 * KB;                        // 64-wide K sub-tiles per operand tile
+  static constexpr int B_HALF_BYTES = B_ROWS * 64 * 2;       // one 64-wide K sub-tile
+  static constexpr int B_STAGE_BYTES = KSUB * B_HALF_BYTES;
+  static constexpr int A_TILE_BYTES = KSUB * A_HALF_BYTES;
   static constexpr int A_BYTES = R * A_TILE_BYTES;
   static constexpr int B_BYTES = STAGES * B_STAGE_BYTES;
   static constexpr int BAR_OFF = A_BYTES + B_BYTES;
@@ -68,11 +74,13 @@ struct TcCfg {
   static constexpr int TILES_PER_GROUP = CG2 ? 2 * R : R;
 };
 
-template <int R, int BN, int STAGES, bool CG2>
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                  const TcParams prm) {
-  using S = TcCfg<R, BN, STAGES, CG2>;
+  using S = TcCfg<R, BN, STAGES, CG2, KB>;
+  constexpr int A_TILE_BYTES = S::A_TILE_BYTES;
+  constexpr int KSUB = S::KSUB;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                             : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
@@ -172,12 +180,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
           if (rank == 0) mbar_expect_tx(bar_a_full, (CG2 ? 2 : 1) * rc * A_TILE_BYTES);
           for (int r = 0; r < rc; ++r) {
             const int tile = group_start(g) + (CG2 ? 2 * r + rank : r);
-            if constexpr (CG2) {
-              tma_load_2d_cg2(sA + r * A_TILE_BYTES, &tmapQ, a_full_tx, 0, tile * 128);
-              tma_load_2d_cg2(sA + r * A_TILE_BYTES + A_HALF_BYTES, &tmapQ, a_full_tx, 64, tile * 128);
-            } else {
-              tma_load_2d(sA + r * A_TILE_BYTES, &tmapQ, a_full_tx, 0, tile * 128);
-              tma_load_2d(sA + r * A_TILE_BYTES + A_HALF_BYTES, &tmapQ, a_full_tx, 64, tile * 128);
+#pragma unroll
+            for (int kk = 0; kk < KSUB; ++kk) {
+              if constexpr (CG2) tma_load_2d_cg2(sA + r * A_TILE_BYTES + kk * A_HALF_BYTES, &tmapQ, a_full_tx, kk * 64, tile * 128);
+              else tma_load_2d(sA + r * A_TILE_BYTES + kk * A_HALF_BYTES, &tmapQ, a_full_tx, kk * 64, tile * 128);
             }
           }
           ++a_loads;
@@ -190,11 +196,13 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
           const uint32_t dst = sB + stage * S::B_STAGE_BYTES;
           if constexpr (CG2) {
             const uint32_t full_tx = mapa_u32(bar_full(stage), 0);
-            tma_load_2d_cg2_hint(dst, &tmapP, full_tx, 0, row, pol);
-            tma_load_2d_cg2_hint(dst + S::B_HALF_BYTES, &tmapP, full_tx, 64, row, pol);
+#pragma unroll
+            for (int kk = 0; kk < KSUB; ++kk)
+              tma_load_2d_cg2_hint(dst + kk * S::B_HALF_BYTES, &tmapP, full_tx, kk * 64, row, pol);
           } else {
-            tma_load_2d_hint(dst, &tmapP, bar_full(stage), 0, row, pol);
-            tma_load_2d_hint(dst + S::B_HALF_BYTES, &tmapP, bar_full(stage), 64, row, pol);
+#pragma unroll
+            for (int kk = 0; kk < KSUB; ++kk)
+              tma_load_2d_hint(dst + kk * S::B_HALF_BYTES, &tmapP, bar_full(stage), kk * 64, row, pol);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -244,7 +252,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             const uint32_t d_tmem = tmem_base + buf * BN;
             const uint32_t a_base = sA + r * A_TILE_BYTES;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4 * KSUB; ++k) {
               const uint64_t da = make_sw128_desc(a_base + (k >> 2) * A_HALF_BYTES + (k & 3) * 32);
               const uint64_t db = make_sw128_desc(b_base + (k >> 2) * S::B_HALF_BYTES + (k & 3) * 32);
               if constexpr (CG2) mma_bf16_ss_cg2(d_tmem, da, db, IDESC, k > 0);
@@ -321,11 +329,15 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       int p = p0;                     // current page
       int pe = __shfl_sync(0xffffffffu, pe_cache, 0);
       float runmax[R];
+      int best_chunk[R];                 // AM: item-relative chunk holding the running max ...
+      int best_pos[R];                   // ... and the winner's position inside that chunk
 #pragma unroll
-      for (int r = 0; r < R; ++r) runmax[r] = -INFINITY;
+      for (int r = 0; r < R; ++r) { runmax[r] = -INFINITY; best_chunk[r] = 0; best_pos[r] = 0; }
+      int pstart = 0;                    // AM: item-relative first chunk of the current page
 
       for (int t = 0; t < ntile; ++t) {
         const int p_save = p;
+        const int pstart_save = pstart;
         const int ch_tile0 = t * CH_PER_TILE;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -333,6 +345,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             // every query tile walks the same chunks of this page tile
             if (p != p_save) {
               p = p_save;
+              pstart = pstart_save;
               const int b = (p - p0) >> 5;
               if (b != cb) { cb = b; pe_cache = load_pe(b); }
               pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
@@ -342,10 +355,20 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             tc_fence_after();
             const uint32_t t_addr = t_lane + buf * BN;
             float rm = runmax[r];
+            int bc = best_chunk[r], bp = best_pos[r];
             // page complete for this query tile: mask, reduce the 32 query tokens, store, next page
             auto finalize = [&]() {
-              const float s = warp_sum(rm * qm[r]);
-              if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
+              if constexpr (AM) {
+                // winning packed slot of this (query token, page): chunk within the page * 16 + position
+                const int slot = (bc - pstart) * EVDR_CHUNK + bp;
+                if (qidx[r] >= 0 && lane < prm.lq)
+                  prm.argmax[(size_t)p * ((size_t)prm.nq * prm.lq) + (size_t)qidx[r] * prm.lq + lane] = slot;
+                pstart = pe;
+                bc = pe;
+              } else {
+                const float s = warp_sum(rm * qm[r]);
+                if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
+              }
               rm = -INFINITY;
               ++p;
               const int b = (p - p0) >> 5;
@@ -357,6 +380,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             // go through the FMNMX3 trees.  The buffer goes back to the MMA warp as soon as the
             // last load has landed, before any page logic.
             float h[CH_PER_TILE];
+            int hp[AM ? CH_PER_TILE : 1];   // AM: first position of the chunk max inside its chunk
             {
               float va[32], vb[32];
               tmem_ld32_issue(t_addr, va);
@@ -366,16 +390,25 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                 tmem_ld32_issue(t_addr + (grp + 1) * 32, vb);
                 h[2 * grp] = max16(va, 0);
                 h[2 * grp + 1] = max16(va, 16);
+                if constexpr (AM) {
+                  hp[2 * grp] = first_pos16(va, 0, h[2 * grp]);
+                  hp[2 * grp + 1] = first_pos16(va, 16, h[2 * grp + 1]);
+                }
                 tmem_wait_ld_tied(vb);
                 if (grp + 2 < BN / 32) tmem_ld32_issue(t_addr + (grp + 2) * 32, va);
                 else release_tmem(buf);
                 h[2 * grp + 2] = max16(vb, 0);
                 h[2 * grp + 3] = max16(vb, 16);
+                if constexpr (AM) {
+                  hp[2 * grp + 2] = first_pos16(vb, 0, h[2 * grp + 2]);
+                  hp[2 * grp + 3] = first_pos16(vb, 16, h[2 * grp + 3]);
+                }
                 if (grp + 2 < BN / 32) tmem_wait_ld_tied(va);
               }
             }
             // ---- fold the chunk maxes into the running per-page max; a page can end after any chunk
-            if (pe >= ch_tile0 + CH_PER_TILE) {
+            const bool whole_tile = !AM && (pe >= ch_tile0 + CH_PER_TILE);
+            if (whole_tile) {
               float m = rm;
 #pragma unroll
               for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, h[j], h[j + 1]);
@@ -390,13 +423,24 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               while (lo < CH_PER_TILE) {
                 const int hi = min(pe - ch_tile0, CH_PER_TILE);   // pe is INT_MAX past the item's end
 #pragma unroll
-                for (int j = 0; j < CH_PER_TILE; ++j)
-                  rm = (j >= lo && j < hi) ? fmaxf(rm, h[j]) : rm;
+                for (int j = 0; j < CH_PER_TILE; ++j) {
+                  if constexpr (AM) {
+                    // strict '>' in ascending chunk order keeps the first chunk attaining the max
+                    const bool take = (j >= lo && j < hi) && (h[j] > rm);
+                    rm = take ? h[j] : rm;
+                    bc = take ? ch_tile0 + j : bc;
+                    bp = take ? hp[j] : bp;
+                  } else {
+                    rm = (j >= lo && j < hi) ? fmaxf(rm, h[j]) : rm;
+                  }
+                }
                 if (pe - ch_tile0 <= CH_PER_TILE) finalize();
                 lo = hi;
               }
             }
             runmax[r] = rm;
+            best_chunk[r] = bc;
+            best_pos[r] = bp;
             ++acc_it;
           }
         }
@@ -416,9 +460,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
 }
 
 static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uint64_t rows,
-                          uint32_t box_rows, const char* what) {
-  cuuint64_t dims[2] = {(cuuint64_t)EVDR_TC_DIM, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)EVDR_TC_DIM * 2};
+                          uint32_t box_rows, int kb, const char* what) {
+  cuuint64_t dims[2] = {(cuuint64_t)EVDR_TC_DIM * kb, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)EVDR_TC_DIM * 2 * kb};
   cuuint32_t box[2] = {64u, box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = h->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
@@ -430,16 +474,16 @@ static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uin
   return EVDR_OK;
 }
 
-template <int R, int BN, int STAGES, bool CG2>
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1>
 static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens,
                      TcParams prm, cudaStream_t st) {
-  using S = TcCfg<R, BN, STAGES, CG2>;
+  using S = TcCfg<R, BN, STAGES, CG2, KB>;
   CUtensorMap tmQ, tmP;
-  int rc = encode_2d_bf16(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, 128, "queries");
+  int rc = encode_2d_bf16(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, 128, KB, "queries");
   if (rc != EVDR_OK) return rc;
-  rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, "page tokens");
+  rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, KB, "page tokens");
   if (rc != EVDR_OK) return rc;
-  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2>;
+  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB>;
   if ((size_t)S::TOTAL > h->smem_optin)
     return set_error(EVDR_ERR_UNSUPPORTED, "tensor-core kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -463,12 +507,11 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
   prm.sched = nullptr;
-  if (!CG2) {  // stream-ordered 4-byte item counter, zeroed for this launch
-    EVDR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prm.sched), sizeof(int), st));
+  if (!CG2) {  // this launch's item counter: next slot of the handle's ring, zeroed on the stream
+    prm.sched = h->sched_ring + (h->sched_next++ % EVDR_SCHED_RING);
     EVDR_CUDA(cudaMemsetAsync(prm.sched, 0, sizeof(int), st));
   }
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmQ, tmP, prm);
-  if (prm.sched) cudaFreeAsync(prm.sched, st);
   if (le != cudaSuccess)
     return set_error(EVDR_ERR_CUDA, "launch of maxsim_tc_kernel failed: %s", cudaGetErrorString(le));
   return EVDR_OK;
@@ -478,13 +521,15 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
 
 using namespace evdr;
 
-extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,
-                                      const void* tokens, int64_t n_tokens,
-                                      const int32_t* chunk_off, int np, int64_t total_chunks,
-                                      int pages_per_item, float* out, int64_t out_ld, void* stream) {
+static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,
+                           const void* tokens, int64_t n_tokens, const int32_t* chunk_off, int np,
+                           int64_t total_chunks, int pages_per_item, float* out, int64_t out_ld,
+                           int32_t* argmax, int lq, int k_blocks, void* stream) {
+  if (k_blocks != 1 && k_blocks != 3)
+    return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed: k_blocks=%d (1 = bf16, 3 = bf16x3 split)", k_blocks);
   EVDR_REQUIRE_HANDLE(h);
-  EVDR_CHECK_ARG(Qb && qmask32 && tokens && chunk_off && out, "evdr_maxsim_packed_fwd: null pointer");
-  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && out_ld >= np, "evdr_maxsim_packed_fwd: bad shape nq=%d np=%d ld=%lld",
+  EVDR_CHECK_ARG(Qb && qmask32 && tokens && chunk_off && (out || argmax), "evdr_maxsim_packed: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && (argmax || out_ld >= np), "evdr_maxsim_packed: bad shape nq=%d np=%d ld=%lld",
                  nq, np, (long long)out_ld);
   EVDR_CHECK_ARG(total_chunks >= np && n_tokens >= total_chunks * EVDR_CHUNK,
                  "evdr_maxsim_packed_fwd: token stream (%lld) shorter than %lld chunks",
@@ -497,6 +542,8 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
   prm.chunk_off = chunk_off;
   prm.out = out;
   prm.out_ld = out_ld;
+  prm.argmax = argmax;
+  prm.lq = lq;
   prm.nq = nq;
   prm.np = np;
   prm.nqt = (nq + 3) / 4;
@@ -505,10 +552,12 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
   const bool want_pair = mode && strcmp(mode, "pair") == 0;
   // single-CTA tiles are the default: measured 1443 vs 1282 TFLOP/s for CTA pairs at 1024 queries
   // (profiles/): both are power-capped, the pair hand-offs cross the cluster and cost utilisation
-  const bool pair = want_pair && prm.nqt >= 2;
+  const bool pair = want_pair && prm.nqt >= 2 && argmax == nullptr && k_blocks == 1;
   int R, tpg;
   if (pair) { R = (prm.nqt + 1) / 2; if (R > 4) R = 4; tpg = 2 * R; }
   else { R = prm.nqt >= 3 ? 3 : prm.nqt; tpg = R; }
+  if (argmax) { R = 3; tpg = 3; }   // the argmax variant is instantiated for R = 3 only
+  if (k_blocks == 3) { R = 1; tpg = 1; }   // bf16x3: one resident query tile (96 KB), 64-token page tiles
   const int n_qgroups = (prm.nqt + tpg - 1) / tpg;
   const int units = pair ? h->sm_count / 2 : h->sm_count;
   int ppi = pages_per_item;
@@ -522,7 +571,7 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
     // ... but the `units` items in flight span units / n_qgroups page blocks, which must stay
     // L2-resident (126 MB) for the other query groups' re-reads to hit: cap the window at ~48 MB
     if (n_qgroups > 1) {
-      const double cap = 48e6 * n_qgroups / ((double)units * avg_tok * EVDR_TC_DIM * 2);
+      const double cap = 48e6 * n_qgroups / ((double)units * avg_tok * EVDR_TC_DIM * 2 * k_blocks);
       if (ppi > cap) ppi = cap < 8.0 ? 8 : (int)cap;   // >= 8 pages: keep the query-tile reload amortised
     }
     if (ppi >= 16) ppi = (ppi / 16) * 16;
@@ -537,6 +586,11 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
   prm.g_rem = prm.nqt % n_qgroups;
   prm.stream_hint = (n_qgroups == 1) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k_blocks == 3) {
+    if (argmax) return launch_tc<1, 64, 2, false, true, 3>(h, Qb, tokens, n_tokens, prm, st);
+    return launch_tc<1, 64, 2, false, false, 3>(h, Qb, tokens, n_tokens, prm, st);
+  }
+  if (argmax) return launch_tc<3, 256, 2, false, true>(h, Qb, tokens, n_tokens, prm, st);
   if (pair) {
     if (R == 1) return launch_tc<1, 256, 6, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 2) return launch_tc<2, 256, 5, true>(h, Qb, tokens, n_tokens, prm, st);
@@ -546,4 +600,24 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
   if (R == 1) return launch_tc<1, 256, 3, false>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 2) return launch_tc<2, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
   return launch_tc<3, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
+}
+
+extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,
+                                      const void* tokens, int64_t n_tokens,
+                                      const int32_t* chunk_off, int np, int64_t total_chunks,
+                                      int pages_per_item, int k_blocks, float* out, int64_t out_ld,
+                                      void* stream) {
+  if (!out) return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed_fwd: out is null");
+  return packed_dispatch(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks,
+                         pages_per_item, out, out_ld, nullptr, EVDR_TC_LQ, k_blocks, stream);
+}
+
+extern "C" int evdr_maxsim_packed_argmax(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,
+                                         int lq, const void* tokens, int64_t n_tokens,
+                                         const int32_t* chunk_off, int np, int64_t total_chunks,
+                                         int k_blocks, int32_t* argmax_slots, void* stream) {
+  if (!argmax_slots) return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed_argmax: argmax_slots is null");
+  if (lq < 1 || lq > EVDR_TC_LQ) return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed_argmax: lq=%d outside [1,32]", lq);
+  return packed_dispatch(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, 0, nullptr,
+                         0, argmax_slots, lq, k_blocks, stream);
 }

@@ -13,6 +13,21 @@ namespace evdr {
 
 constexpr int CH = EVDR_CHUNK;
 
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  return o;
+}
+// v - float(bf16(v)): the part of v the bf16 rounding dropped (exact in fp32)
+__device__ __forceinline__ float4 residual_bf16x4(float4 v, uint2 hi) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.y));
+  return make_float4(v.x - a.x, v.y - a.y, v.z - b.x, v.w - b.y);
+}
+
 // n_chunks[c]; varlen: ceil((last valid + 1)/16), min 1; else ceil(lp/16)
 __global__ void __launch_bounds__(256)
 plan_len_kernel(const uint8_t* __restrict__ pmask, int np, int lp, int varlen,
@@ -80,7 +95,7 @@ plan_scan_kernel(const int32_t* __restrict__ nch, int np, int32_t* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
-                  const int32_t* __restrict__ chunk_off, int np, int lp, int normalize,
+                  const int32_t* __restrict__ chunk_off, int np, int lp, int normalize, int kb,
                   __nv_bfloat16* __restrict__ tokens) {
   extern __shared__ int src[];  // n_slots ints
   __shared__ int seg_last[256];
@@ -123,7 +138,8 @@ pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
   }
   __syncthreads();
 
-  __nv_bfloat16* dst = tokens + (size_t)c0 * CH * EVDR_TC_DIM;
+  const int row = EVDR_TC_DIM * kb;        // kb = 3: [hi | lo | hi] rows of the bf16x3 split
+  __nv_bfloat16* dst = tokens + (size_t)c0 * CH * row;
   const T* Pc = P + (size_t)c * lp * EVDR_TC_DIM;
   for (int m = warp; m < n_slots; m += (blockDim.x >> 5)) {
     const int s = src[m];
@@ -137,18 +153,19 @@ pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
         v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
       }
     }
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-    __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&lo);
-    o.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(dst + (size_t)m * EVDR_TC_DIM + lane * 4) = o;
+    const uint2 hi = pack_bf16x4(v);
+    *reinterpret_cast<uint2*>(dst + (size_t)m * row + lane * 4) = hi;
+    if (kb == 3) {
+      const uint2 lo = pack_bf16x4(residual_bf16x4(v, hi));
+      *reinterpret_cast<uint2*>(dst + (size_t)m * row + EVDR_TC_DIM + lane * 4) = lo;
+      *reinterpret_cast<uint2*>(dst + (size_t)m * row + 2 * EVDR_TC_DIM + lane * 4) = hi;
+    }
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-pack_queries_kernel(const T* __restrict__ Q, const uint8_t* __restrict__ qmask, int nq, int lq,
+pack_queries_kernel(const T* __restrict__ Q, const uint8_t* __restrict__ qmask, int nq, int lq, int kb,
                     __nv_bfloat16* __restrict__ Qb, uint8_t* __restrict__ qmask32) {
   const int lane = threadIdx.x & 31;
   const long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -157,12 +174,14 @@ pack_queries_kernel(const T* __restrict__ Q, const uint8_t* __restrict__ qmask, 
   const bool valid = (n < lq) && qmask[(size_t)q * lq + n] != 0;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (valid) v = load4(Q + ((size_t)q * lq + n) * EVDR_TC_DIM + lane * 4);
-  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-  __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-  uint2 o;
-  o.x = *reinterpret_cast<uint32_t*>(&lo);
-  o.y = *reinterpret_cast<uint32_t*>(&hi);
-  *reinterpret_cast<uint2*>(Qb + (size_t)slot * EVDR_TC_DIM + lane * 4) = o;
+  const int row = EVDR_TC_DIM * kb;        // kb = 3: [hi | hi | lo] rows of the bf16x3 split
+  const uint2 hi = pack_bf16x4(v);
+  *reinterpret_cast<uint2*>(Qb + (size_t)slot * row + lane * 4) = hi;
+  if (kb == 3) {
+    const uint2 lo = pack_bf16x4(residual_bf16x4(v, hi));
+    *reinterpret_cast<uint2*>(Qb + (size_t)slot * row + EVDR_TC_DIM + lane * 4) = hi;
+    *reinterpret_cast<uint2*>(Qb + (size_t)slot * row + 2 * EVDR_TC_DIM + lane * 4) = lo;
+  }
   if (lane == 0) qmask32[slot] = valid ? 1 : 0;
 }
 
@@ -254,12 +273,13 @@ int evdr_pack_plan(evdr_handle* h, const uint8_t* pmask, int np, int lp, int var
 }
 
 int evdr_pack_pages(evdr_handle* h, const void* P, int p_dtype, const uint8_t* pmask,
-                    const int32_t* chunk_off, int np, int lp, int d, int normalize,
+                    const int32_t* chunk_off, int np, int lp, int d, int normalize, int k_blocks,
                     void* tokens, void* stream) {
   EVDR_REQUIRE_HANDLE(h);
   EVDR_CHECK_ARG(P && pmask && chunk_off && tokens, "evdr_pack_pages: null pointer");
   EVDR_CHECK_ARG(d == EVDR_TC_DIM, "evdr_pack_pages: d=%d, the tensor-core path needs d=128", d);
   EVDR_CHECK_ARG(np >= 1 && lp >= 1, "evdr_pack_pages: bad shape");
+  EVDR_CHECK_ARG(k_blocks == 1 || k_blocks == 3, "evdr_pack_pages: k_blocks=%d (1 or 3)", k_blocks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // upper bound of slots per page: rect plan gives ceil(lp/16)*16, varlen never more
   size_t smem = sizeof(int) * (size_t)((lp + CH - 1) / CH) * CH;
@@ -268,11 +288,11 @@ int evdr_pack_pages(evdr_handle* h, const void* P, int p_dtype, const uint8_t* p
   if (p_dtype == EVDR_F32) {
     EVDR_CUDA(cudaFuncSetAttribute(pack_pages_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pack_pages_kernel<float><<<np, 256, smem, st>>>(static_cast<const float*>(P), pmask, chunk_off, np,
-                                                   lp, normalize, static_cast<__nv_bfloat16*>(tokens));
+                                                   lp, normalize, k_blocks, static_cast<__nv_bfloat16*>(tokens));
   } else if (p_dtype == EVDR_BF16) {
     EVDR_CUDA(cudaFuncSetAttribute(pack_pages_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pack_pages_kernel<__nv_bfloat16><<<np, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(P), pmask,
-                                                           chunk_off, np, lp, normalize,
+                                                           chunk_off, np, lp, normalize, k_blocks,
                                                            static_cast<__nv_bfloat16*>(tokens));
   } else {
     return set_error(EVDR_ERR_INVALID, "evdr_pack_pages: bad dtype %d", p_dtype);
@@ -282,22 +302,23 @@ int evdr_pack_pages(evdr_handle* h, const void* P, int p_dtype, const uint8_t* p
 }
 
 int evdr_pack_queries(evdr_handle* h, const void* Q, int q_dtype, const uint8_t* qmask, int nq,
-                      int lq, int d, void* Qb, uint8_t* qmask32, void* stream) {
+                      int lq, int d, int k_blocks, void* Qb, uint8_t* qmask32, void* stream) {
   EVDR_REQUIRE_HANDLE(h);
   EVDR_CHECK_ARG(Q && qmask && Qb && qmask32, "evdr_pack_queries: null pointer");
   EVDR_CHECK_ARG(d == EVDR_TC_DIM, "evdr_pack_queries: d=%d, the tensor-core path needs d=128", d);
   if (lq > EVDR_TC_LQ)
     return set_error(EVDR_ERR_UNSUPPORTED, "evdr_pack_queries: lq=%d > 32 (use evdr_maxsim_fwd)", lq);
   EVDR_CHECK_ARG(nq >= 1 && lq >= 1, "evdr_pack_queries: bad shape");
+  EVDR_CHECK_ARG(k_blocks == 1 || k_blocks == 3, "evdr_pack_queries: k_blocks=%d (1 or 3)", k_blocks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long slots = (long long)nq * EVDR_TC_LQ;
   unsigned grid = (unsigned)((slots + 7) / 8);
   if (q_dtype == EVDR_F32)
-    pack_queries_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(Q), qmask, nq, lq,
+    pack_queries_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(Q), qmask, nq, lq, k_blocks,
                                                     static_cast<__nv_bfloat16*>(Qb), qmask32);
   else if (q_dtype == EVDR_BF16)
     pack_queries_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(Q), qmask,
-                                                            nq, lq, static_cast<__nv_bfloat16*>(Qb),
+                                                            nq, lq, k_blocks, static_cast<__nv_bfloat16*>(Qb),
                                                             qmask32);
   else
     return set_error(EVDR_ERR_INVALID, "evdr_pack_queries: bad dtype %d", q_dtype);

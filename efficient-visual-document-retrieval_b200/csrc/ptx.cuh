@@ -263,6 +263,13 @@ __device__ __forceinline__ float max16(const float (&v)[32], int o) {
   const float a4 = max3(v[o + 12], v[o + 13], v[o + 14]);
   return fmaxf(max3(a0, a1, a2), max3(a3, a4, v[o + 15]));
 }
+// first position i in [0,16) with v[o+i] == m (m is the exact max of those 16 values)
+__device__ __forceinline__ int first_pos16(const float (&v)[32], int o, float m) {
+  int pos = 15;
+#pragma unroll
+  for (int i = 14; i >= 0; --i) pos = (v[o + i] == m) ? i : pos;
+  return pos;
+}
 // max(rm, v[o..o+15]): 8 FMNMX3, depth 3
 __device__ __forceinline__ float max_tree16(float rm, const float (&v)[32], int o) {
   const float a0 = max3(v[o + 0], v[o + 1], v[o + 2]);

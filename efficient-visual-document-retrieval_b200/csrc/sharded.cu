@@ -78,6 +78,7 @@ int evdr_destroy(evdr_handle* h) {
     if (api) api->CommDestroy(static_cast<nccl_comm_t>(h->nccl_comm));
     h->nccl_comm = nullptr;
   }
+  if (h->sched_ring) cudaFree(h->sched_ring);
   delete h;
   return EVDR_OK;
 }

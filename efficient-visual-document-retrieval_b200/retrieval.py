@@ -97,21 +97,68 @@ class _MaxSimExactFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        Q, P, qm, pm, am = ctx.saved_tensors
-        need_q, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        return _backward_through_argmax(ctx, g)
+
+
+def _backward_through_argmax(ctx, g):
+    Q, P, qm, pm, am = ctx.saved_tensors
+    need_q, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    nq, lq, d = Q.shape
+    npg, lp, _ = P.shape
+    dev = Q.device
+    g = g.to(torch.float32).contiguous()
+    dP = torch.empty((npg, lp, d), dtype=torch.float32, device=dev) if need_p else None
+    dQ = torch.empty((nq, lq, d), dtype=torch.float32, device=dev) if need_q else None
+    if need_p or need_q:
+        lib = _lib.load()
+        _lib.check(lib.evdr_maxsim_bwd(_lib.handle(dev), g.data_ptr(), Q.data_ptr(), _lib.dtype_code(Q),
+                                       P.data_ptr(), _lib.dtype_code(P), qm.data_ptr(), pm.data_ptr(),
+                                       am.data_ptr(), nq, npg, lq, lp, d, _lib.ptr(dP), _lib.ptr(dQ),
+                                       _lib.stream_ptr(dev)), "evdr_maxsim_bwd")
+    return (None if dQ is None else dQ.to(Q.dtype), None if dP is None else dP.to(P.dtype), None, None)
+
+
+class _MaxSimRescoreFn(torch.autograd.Function):
+    """Gradient calls on ColPali shapes: tcgen05 search for the winning page token of every
+    (query token, page) on bf16 operands, then exact fp32 rescoring of the winners on the original
+    operands (evdr_maxsim_packed_argmax + evdr_maxsim_rescore); the backward scatters through the same
+    indices.  Equal to the exact path wherever bf16 and fp32 pick the same token."""
+
+    @staticmethod
+    def forward(ctx, Q, P, qm, pm):
         nq, lq, d = Q.shape
         npg, lp, _ = P.shape
         dev = Q.device
-        g = g.to(torch.float32).contiguous()
-        dP = torch.empty((npg, lp, d), dtype=torch.float32, device=dev) if need_p else None
-        dQ = torch.empty((nq, lq, d), dtype=torch.float32, device=dev) if need_q else None
-        if need_p or need_q:
-            lib = _lib.load()
-            _lib.check(lib.evdr_maxsim_bwd(_lib.handle(dev), g.data_ptr(), Q.data_ptr(), _lib.dtype_code(Q),
-                                           P.data_ptr(), _lib.dtype_code(P), qm.data_ptr(), pm.data_ptr(),
-                                           am.data_ptr(), nq, npg, lq, lp, d, _lib.ptr(dP), _lib.ptr(dQ),
-                                           _lib.stream_ptr(dev)), "evdr_maxsim_bwd")
-        return (None if dQ is None else dQ.to(Q.dtype), None if dP is None else dP.to(P.dtype), None, None)
+        lib = _lib.load()
+        h = _lib.handle(dev)
+        st = _lib.stream_ptr(dev)
+        # bf16x3 split operands: the search runs at ~fp32 accuracy, so the winners are the reference's
+        Qb, qm32 = pack_queries(Q, qm, 3)
+        pk = PackedPages.from_padded(P, pm, normalize=False, varlen=False, k_blocks=3)
+        R = nq * lq
+        am = torch.empty((npg, R), dtype=torch.int32, device=dev)
+        _lib.check(lib.evdr_maxsim_packed_argmax(h, Qb.data_ptr(), qm32.data_ptr(), nq, lq, pk.tokens.data_ptr(),
+                                                 pk.tokens.shape[0], pk.chunk_off.data_ptr(), npg,
+                                                 pk.total_chunks, 3, am.data_ptr(), st), "evdr_maxsim_packed_argmax")
+        out = torch.empty((nq, npg), dtype=torch.float32, device=dev)
+        blk = max(1, min(65535, npg, _EXACT_WS_BYTES // (4 * R)))
+        ws = torch.empty((blk, R), dtype=torch.float32, device=dev)
+        single = blk >= npg
+        qd, pd = _lib.dtype_code(Q), _lib.dtype_code(P)
+        for c0 in range(0, npg, blk):
+            c1 = min(npg, c0 + blk)
+            o = out if single else torch.empty((nq, c1 - c0), dtype=torch.float32, device=dev)
+            _lib.check(lib.evdr_maxsim_rescore(h, Q.data_ptr(), qd, P[c0:c1].data_ptr(), pd, qm.data_ptr(),
+                                               pm[c0:c1].data_ptr(), am[c0:c1].data_ptr(), nq, c1 - c0, lq, lp,
+                                               d, ws.data_ptr(), o.data_ptr(), st), "evdr_maxsim_rescore")
+            if not single:
+                out[:, c0:c1] = o
+        ctx.save_for_backward(Q, P, qm, pm, am)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return _backward_through_argmax(ctx, g)
 
 
 def maxsim_exact(Q, P, qmask, pmask) -> torch.Tensor:
@@ -176,10 +223,13 @@ def score_multi_vector_masked(
     Returns a new fp32 (Q, P) tensor on the inputs' device.  ``chunk_p`` is accepted and ignored
     (the reference's outputs do not depend on it and nothing is materialised here).
 
-    precision=None | "bf16": tcgen05 path (bf16 operands, fp32 accumulation) whenever D == 128,
-    Lq <= 32 and no gradient is required.  precision="fp32" (or env EVDR_PRECISION=fp32), other
-    shapes, and calls that need a gradient use the exact fp32 kernels, whose backward is the
-    deterministic closed form of the reference's autograd.
+    precision=None | "bf16": tcgen05 path (bf16 operands, fp32 accumulation) whenever D == 128 and
+    Lq <= 32.  Calls that need a gradient use the same tensor-core kernel to FIND the winning page
+    token of every (query token, page) and rescore the winners exactly in fp32 on the original
+    operands, so the student scores of a training step are fp32-exact wherever bf16 and fp32 agree on
+    the winner; the backward is the deterministic closed form of the reference's autograd through
+    those indices.  precision="fp32" (or env EVDR_PRECISION=fp32) and other shapes use the exact fp32
+    kernels throughout.
     """
     if Q.dim() != 3 or P.dim() != 3 or Q.shape[-1] != P.shape[-1]:
         raise ValueError(f"expected Q (Q,Lq,D) and P (P,Lp,D), got {tuple(Q.shape)} and {tuple(P.shape)}")
@@ -195,8 +245,16 @@ def score_multi_vector_masked(
         return torch.zeros((nq, npg), dtype=torch.float32, device=Q.device)
     precision = precision or os.environ.get("EVDR_PRECISION", "bf16")
     needs_grad = torch.is_grad_enabled() and (Q.requires_grad or P.requires_grad)
-    if precision == "fp32" or needs_grad or d != TC_DIM or lq > TC_LQ:
+    if precision == "fp32" or d != TC_DIM or lq > TC_LQ:
         return maxsim_exact(Q, P, qmask, pmask)
+    if precision == "bf16x3" and not needs_grad:
+        # high-fidelity tensor-core mode for operands that are not bf16-representable
+        with torch.no_grad():
+            Qb, qm32 = pack_queries(Q, qmask, 3)
+            return PackedPages.from_padded(P.detach(), pmask, k_blocks=3).score_packed(Qb, qm32)
+    if needs_grad:
+        # training: tensor-core search + fp32 rescoring of the winners, backward through the same indices
+        return _MaxSimRescoreFn.apply(_float_operand(Q), _float_operand(P), _mask_u8(qmask), _mask_u8(pmask))
     with torch.no_grad():
         Qb, qm32 = pack_queries(Q, qmask)
         return _packed_for(P.detach(), pmask).score_packed(Qb, qm32)

@@ -117,17 +117,20 @@ EVDR_API int evdr_maxsim_bwd(evdr_handle* h,
  *   as evaluator/retrieval.py:192,204).  normalize != 0 fuses the reference's
  *   `l2_normalize(P * pmask[...,None])` (utils/preprocess_data.py:8-9,
  *   mainv2_iter_listwise.py:280) in fp32 before the bf16 rounding.
+ * k_blocks: 1 = plain bf16 rows of 128; 3 = the bf16x3 split for near-fp32 fidelity: page rows are
+ *   [hi | lo | hi] and query rows [hi | hi | lo] of 384 bf16 (hi = bf16(x), lo = bf16(x - hi)), whose
+ *   K = 384 contraction is Qhi.Phi + Qhi.Plo + Qlo.Phi = <Q,P> up to a 2^-18 relative term.
  * ------------------------------------------------------------------------ */
 EVDR_API int evdr_pack_plan(evdr_handle* h, const uint8_t* pmask_dev, int np, int lp,
                             int varlen, int32_t* chunk_off_dev, void* stream);
 EVDR_API int evdr_pack_pages(evdr_handle* h, const void* P_dev, int p_dtype,
                              const uint8_t* pmask_dev, const int32_t* chunk_off_dev,
-                             int np, int lp, int d, int normalize,
+                             int np, int lp, int d, int normalize, int k_blocks,
                              void* tokens_bf16_dev, void* stream);
 /* Queries for the tensor-core path: bf16 [nq, 32, 128], masked / padded token
  * slots zeroed; qmask32 [nq, 32] uint8.  Requires lq <= 32, d == 128. */
 EVDR_API int evdr_pack_queries(evdr_handle* h, const void* Q_dev, int q_dtype,
-                               const uint8_t* qmask_dev, int nq, int lq, int d,
+                               const uint8_t* qmask_dev, int nq, int lq, int d, int k_blocks,
                                void* Qb_bf16_dev, uint8_t* qmask32_dev, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -135,8 +138,8 @@ EVDR_API int evdr_pack_queries(evdr_handle* h, const void* Q_dev, int q_dtype,
  * row-max over page tokens and the query-token sum are fused into the epilogue,
  * the similarity matrix never leaves the SM.  Persistent kernel, one CTA per SM.
  *
- *   tokens_dev : bf16 [n_tokens, 128], n_tokens >= 16*chunk_off[np] (the stream);
- *   Qb_dev     : bf16 [nq, 32, 128] from evdr_pack_queries;
+ *   tokens_dev : bf16 [n_tokens, 128*k_blocks], n_tokens >= 16*chunk_off[np] (the stream);
+ *   Qb_dev     : bf16 [nq, 32, 128*k_blocks] from evdr_pack_queries;
  *   out_dev    : fp32 [nq, out_ld], column c = page c.
  * The base addresses must be 16-byte aligned (TMA).  `pages_per_item` <= 0 lets
  * the library pick the work-item size.
@@ -145,8 +148,28 @@ EVDR_API int evdr_maxsim_packed_fwd(evdr_handle* h,
                                     const void* Qb_dev, const uint8_t* qmask32_dev, int nq,
                                     const void* tokens_dev, int64_t n_tokens,
                                     const int32_t* chunk_off_dev, int np,
-                                    int64_t total_chunks, int pages_per_item,
+                                    int64_t total_chunks, int pages_per_item, int k_blocks,
                                     float* out_dev, int64_t out_ld, void* stream);
+
+/* Gradient calls: tensor-core search + fp32 rescoring.
+ * evdr_maxsim_packed_argmax runs the same tcgen05 kernel but emits, instead of scores, the packed
+ *   slot attaining each max: argmax_slots_dev int32, PAGE-MAJOR [np, nq*lq] (position inside the
+ *   page's chunks; chosen on bf16 operands with a 2^-19 selection tolerance).
+ * evdr_maxsim_rescore maps every slot back to the page token it holds (fillers -> the valid token
+ *   they duplicate), overwrites argmax_dev with token indices, recomputes exactly those
+ *   <Q[q,n],P[c,m*]> in fp32 on the ORIGINAL operands and reduces them like evdr_maxsim_fwd.  The
+ *   result equals the exact path wherever bf16 and fp32 agree on the winner (elsewhere it is lower
+ *   by at most the bf16 near-tie gap); evdr_maxsim_bwd consumes the same argmax_dev. */
+EVDR_API int evdr_maxsim_packed_argmax(evdr_handle* h,
+                                       const void* Qb_dev, const uint8_t* qmask32_dev, int nq, int lq,
+                                       const void* tokens_dev, int64_t n_tokens,
+                                       const int32_t* chunk_off_dev, int np, int64_t total_chunks,
+                                       int k_blocks, int32_t* argmax_slots_dev, void* stream);
+EVDR_API int evdr_maxsim_rescore(evdr_handle* h,
+                                 const void* Q_dev, int q_dtype, const void* P_dev, int p_dtype,
+                                 const uint8_t* qmask_dev, const uint8_t* pmask_dev,
+                                 int32_t* argmax_dev, int nq, int np, int lq, int lp, int d,
+                                 float* rowmax_ws_dev, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------
  * A7  evaluation tail: top-k and trec_eval-style measures on device

@@ -96,6 +96,7 @@ def test_config5_training_step(evdr, cuda, npg, ls):
     t_got, s_got, loss_got, g_got = step(lambda *a: evdr.score_multi_vector_masked(*a, 64),
                                          lambda x, m: evdr.l2_normalize_masked(x, m))
     U.assert_scores_close(t_got.cpu().numpy(), t_ref.cpu().numpy())
+    # student scores: bf16x3 tensor-core search + fp32 rescoring of the winners
     np.testing.assert_allclose(s_got.cpu().numpy(), s_ref.cpu().numpy(), rtol=2e-5, atol=2e-5)
     assert abs(loss_got.item() - loss_ref.item()) <= 2e-3 * max(1.0, abs(loss_ref.item()))
     # masked student tokens receive exactly zero gradient (the invariant mainv1.py:74-87 prints)
@@ -127,3 +128,52 @@ def test_config1_docvqa_end_to_end(evdr, cuda):
     assert have["NDCG"]["NDCG@5"] == want["NDCG"]["NDCG@5"]
     assert have["Recall"]["Recall@1"] == want["Recall"]["Recall@1"]
     assert 0.3 < want["NDCG"]["NDCG@5"] < 1.0, want["NDCG"]
+
+
+def test_rescore_path_vs_exact_on_fp32_operands(evdr, cuda):
+    """Gradient calls run a bf16x3 (near-fp32) tensor-core search and rescore the winners in fp32.  On
+    operands that are NOT bf16-representable the result must equal the exact fp32 path: same scores,
+    same winners (up to ties at the 1e-6 level), same gradients."""
+    g = torch.Generator(device=cuda).manual_seed(5)
+    npg, ls, nq = 300, 103, 32
+    P = torch.randn(npg, ls, 128, generator=g, device=cuda)
+    pm = torch.rand(npg, ls, generator=g, device=cuda) > 0.15
+    pm[7] = False                                            # an empty page
+    P = evdr.l2_normalize_masked(P, pm)
+    Q = torch.nn.functional.normalize(torch.randn(nq, 32, 128, generator=g, device=cuda), dim=-1)
+    qm = torch.rand(nq, 32, generator=g, device=cuda) > 0.1
+    gout = torch.randn(nq, npg, generator=g, device=cuda)
+    outs, grads = [], []
+    for prec in (None, "fp32"):
+        Pg = P.clone().requires_grad_(True)
+        Qg = Q.clone().requires_grad_(True)
+        o = evdr.score_multi_vector_masked(Qg, Pg, qm, pm, 64, precision=prec)
+        o.backward(gout)
+        outs.append(o.detach())
+        grads.append((Pg.grad, Qg.grad))
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=2e-5, atol=2e-5)
+    assert (outs[0] <= outs[1] + 1e-5).all(), "rescoring a non-winner can only lower a score"
+    assert (outs[0][:, 7] == 0).all() and grads[0][0][7].abs().max() == 0
+    assert grads[0][0][~pm].abs().max() == 0, "masked tokens receive exactly zero gradient"
+    for a, b in zip(grads[0], grads[1]):
+        rel = ((a - b).norm() / b.norm()).item()
+        frac = torch.isclose(a, b, rtol=1e-4, atol=1e-6).float().mean().item()
+        assert rel < 1e-2 and frac > 0.995, (rel, frac)
+
+
+@pytest.mark.parametrize("nq,npg,lp", [(13, 200, 1030), (40, 500, 64), (5, 60, 333)])
+def test_bf16x3_high_fidelity_mode(evdr, cuda, nq, npg, lp):
+    """precision='bf16x3': K = 384 split operands on the tensor cores reproduce the fp32 scores of
+    operands that are not bf16-representable to ~1e-6, where plain bf16 is at ~1e-4."""
+    g = torch.Generator(device=cuda).manual_seed(nq)
+    P = torch.nn.functional.normalize(torch.randn(npg, lp, 128, generator=g, device=cuda), dim=-1)
+    Q = torch.nn.functional.normalize(torch.randn(nq, 32, 128, generator=g, device=cuda), dim=-1)
+    pm = torch.rand(npg, lp, generator=g, device=cuda) > 0.1
+    qm = torch.rand(nq, 32, generator=g, device=cuda) > 0.1
+    exact = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
+    x3 = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="bf16x3")
+    bf = evdr.score_multi_vector_masked(Q, P, qm, pm)
+    e3 = ((x3 - exact).abs() / exact.abs().clamp_min(1)).max().item()
+    e1 = ((bf - exact).abs() / exact.abs().clamp_min(1)).max().item()
+    assert e3 < 5e-6, e3
+    assert e1 < 1e-3 and e3 < e1
