@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--no-extras", action="store_true", help="skip the single-query / 64-query side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--corpus-1m", action="store_true", help="also run the 1M-page top-10 QPS measurement at 2 GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -324,6 +325,15 @@ def main():
             extras = side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus)
         except Exception as e:  # side numbers must never lose the headline line
             extras = {"error": repr(e)}
+        # BASELINE.json configs[3]: top-10 QPS on a 1 M-page corpus sharded over the box (needs the
+        # memory of >= 4 GPUs at 100k pages already resident; 2 GPUs only with --corpus-1m)
+        if n_gpus >= 4 or (n_gpus >= 2 and args.corpus_1m):
+            try:
+                del pk, corpus, pmask, scores, host_scores
+                torch.cuda.empty_cache()
+                extras["corpus_1m"] = corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed)
+            except Exception as e:
+                extras["corpus_1m"] = {"error": repr(e)}
 
     if rank == 0:
         cpu = None
@@ -345,6 +355,40 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed):
+    """Top-10 QPS on a 1,000,000-page corpus (266 GB bf16) sharded by page range over the GPUs of the
+    box: streaming single-query and 64-query batches, local scan + top-10, NCCL all-gather, merge."""
+    total = 1_000_000
+    lo, hi = evdr.partition_pages(total, n_gpus)[rank]
+    npg = hi - lo
+    corpus = evdr.synth.make_uniform_corpus(npg, LP_SLOTS, device=dev, seed=4242 + 1000 * rank)
+    pk = evdr.PackedPages.from_uniform_tokens(corpus, page_offset=lo)
+    search = evdr.ShardedSearch((lo, hi), mode="nccl")
+    out = {"pages_total": total, "pages_per_gpu": npg, "corpus_gb_per_gpu": npg * LP_SLOTS * D * 2 / 1e9}
+    for nq in (1, 64):
+        g = torch.Generator().manual_seed(70 + nq)
+        Q = torch.nn.functional.normalize(torch.randn(nq, LQ, D, generator=g), dim=-1).to(dev)
+        qm = torch.ones((nq, LQ), dtype=torch.bool, device=dev)
+        s = torch.empty((nq, npg), dtype=torch.float32, device=dev)
+
+        def one():
+            Qb, qm32 = evdr.pack_queries(Q, qm)
+            return search.topk(pk.score_packed(Qb, qm32, out=s), TOPK)
+
+        ms = timed(one, 10, 3)
+        rec = {"ms_per_batch": ms, "top10_qps": nq / (ms * 1e-3), "pairs_per_s": nq * total / (ms * 1e-3)}
+        if nq == 1:
+            gbs = npg * BYTES_PER_PAGE / (ms * 1e-3) / 1e9
+            rec["hbm_gbs_per_gpu"] = gbs
+            rec["frac_of_hbm_peak"] = gbs / peaks["hbm_gbs"]
+        else:
+            tf = nq * npg * FLOPS_PER_PAIR / (ms * 1e-3) / 1e12
+            rec["tflops_per_gpu"] = tf
+            rec["frac_of_bf16_burst_peak"] = tf / peaks["bf16_tflops"]
+        out[f"q{nq}"] = rec
+    return out
 
 
 def side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus):
