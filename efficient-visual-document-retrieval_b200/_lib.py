@@ -17,6 +17,7 @@ EVDR_F32, EVDR_BF16 = 0, 1
 CHUNK = 16
 TC_DIM = 128
 TC_LQ = 32
+TC_LQ_MAX = 128      # longer queries are scored as up to 4 groups of 32 tokens
 TOPK_MAX = 128
 
 _lib = None
@@ -39,6 +40,7 @@ _SIGNATURES = {
     "evdr_maxsim_packed_fwd": ([_vp, _vp, _vp, _i, _vp, _i64, _vp, _i, _i64, _i, _i, _vp, _i64, _vp], _i),
     "evdr_maxsim_packed_argmax": ([_vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp], _i),
     "evdr_maxsim_rescore": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "evdr_group_sum": ([_vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp], _i),
     "evdr_topk": ([_vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp], _i),
     "evdr_topk_merge": ([_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
     "evdr_retrieval_metrics": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp], _i),

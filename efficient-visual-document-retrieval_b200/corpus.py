@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import CHUNK, TC_DIM, TC_LQ
+from ._lib import CHUNK, TC_DIM, TC_LQ, TC_LQ_MAX
 
 
 def _mask_u8(mask: torch.Tensor) -> torch.Tensor:
@@ -31,6 +31,35 @@ def _float_operand(t: torch.Tensor) -> torch.Tensor:
     if t.dtype not in (torch.float32, torch.bfloat16):
         t = t.to(torch.float32)
     return t.contiguous()
+
+
+def split_long_queries(Q: torch.Tensor, qmask: torch.Tensor):
+    """Queries longer than 32 tokens -> G = ceil(lq/32) groups of 32 token slots each, returned as
+    (Q (nq*G, 32, d), qmask (nq*G, 32), G).  Exact for MaxSim: the max over page tokens is taken per
+    query token and the per-group scores are added back with evdr_group_sum."""
+    nq, lq, d = Q.shape
+    G = (lq + TC_LQ - 1) // TC_LQ
+    if G == 1:
+        return Q, qmask, 1
+    Qp = torch.zeros((nq, G * TC_LQ, d), dtype=Q.dtype, device=Q.device)
+    mp = torch.zeros((nq, G * TC_LQ), dtype=torch.bool, device=Q.device)
+    Qp[:, :lq] = Q
+    mp[:, :lq] = qmask != 0
+    return Qp.view(nq * G, TC_LQ, d), mp.view(nq * G, TC_LQ), G
+
+
+def group_sum(scores: torch.Tensor, groups: int) -> torch.Tensor:
+    """(nq*groups, np) -> (nq, np): out[q] = sum_g scores[q*groups + g] (evdr_group_sum)."""
+    if groups == 1:
+        return scores
+    rows, npg = scores.shape
+    nq = rows // groups
+    out = torch.empty((nq, npg), dtype=torch.float32, device=scores.device)
+    lib = _lib.load()
+    _lib.check(lib.evdr_group_sum(_lib.handle(scores.device), scores.data_ptr(), scores.stride(0), nq, groups,
+                                  npg, out.data_ptr(), out.stride(0), _lib.stream_ptr(scores.device)),
+               "evdr_group_sum")
+    return out
 
 
 def pack_queries(Q: torch.Tensor, qmask: torch.Tensor, k_blocks: int = 1):
@@ -126,8 +155,10 @@ class PackedPages:
         return out
 
     def score(self, Q: torch.Tensor, qmask: torch.Tensor) -> torch.Tensor:
-        Qb, qm32 = pack_queries(Q, qmask, self.k_blocks)
-        return self.score_packed(Qb, qm32)
+        """MaxSim of (nq, lq <= 128, 128) queries against this shard -> fp32 (nq, n_pages)."""
+        Qs, ms, G = split_long_queries(Q, qmask)
+        Qb, qm32 = pack_queries(Qs, ms, self.k_blocks)
+        return group_sum(self.score_packed(Qb, qm32), G)
 
     def search(self, Q: torch.Tensor, qmask: torch.Tensor, k: int = 10):
         """Top-k pages per query: (scores (nq,k) fp32, ids (nq,k) int64 global page ids)."""

@@ -185,6 +185,19 @@ pack_queries_kernel(const T* __restrict__ Q, const uint8_t* __restrict__ qmask, 
   if (lane == 0) qmask32[slot] = valid ? 1 : 0;
 }
 
+// out[q, c] = sum_g in[(q*G + g), c]: queries longer than 32 tokens are scored as G 32-token groups
+// (the max over page tokens is per query token, so the split is exact); fixed order -> deterministic
+__global__ void __launch_bounds__(256)
+group_sum_kernel(const float* __restrict__ in, long long in_ld, int nq, int G, int np,
+                 float* __restrict__ out, long long out_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nq * np) return;
+  const int q = (int)(i / np), c = (int)(i % np);
+  float s = 0.f;
+  for (int g = 0; g < G; ++g) s += in[((long long)q * G + g) * in_ld + c];
+  out[(long long)q * out_ld + c] = s;
+}
+
 // y = (x*mask)/(||x*mask|| + eps); one warp per token, any d % 4 == 0
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask, long long n_tok,
@@ -323,6 +336,18 @@ int evdr_pack_queries(evdr_handle* h, const void* Q, int q_dtype, const uint8_t*
   else
     return set_error(EVDR_ERR_INVALID, "evdr_pack_queries: bad dtype %d", q_dtype);
   EVDR_LAUNCH_CHECK("pack_queries_kernel");
+  return EVDR_OK;
+}
+
+int evdr_group_sum(evdr_handle* h, const float* in, int64_t in_ld, int nq, int groups, int np,
+                   float* out, int64_t out_ld, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(in && out && nq >= 1 && groups >= 1 && np >= 1 && in_ld >= np && out_ld >= np,
+                 "evdr_group_sum: bad arguments");
+  const long long n = (long long)nq * np;
+  group_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, in_ld, nq, groups, np, out, out_ld);
+  EVDR_LAUNCH_CHECK("group_sum_kernel");
   return EVDR_OK;
 }
 

@@ -21,7 +21,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 import torch
 
 from . import _lib
-from ._lib import TC_DIM, TC_LQ
+from ._lib import TC_DIM, TC_LQ, TC_LQ_MAX
 from .corpus import PackedPages, _float_operand, _mask_u8, pack_queries
 from .topk import retrieval_metrics, topk, topk_metrics
 
@@ -245,19 +245,17 @@ def score_multi_vector_masked(
         return torch.zeros((nq, npg), dtype=torch.float32, device=Q.device)
     precision = precision or os.environ.get("EVDR_PRECISION", "bf16")
     needs_grad = torch.is_grad_enabled() and (Q.requires_grad or P.requires_grad)
-    if precision == "fp32" or d != TC_DIM or lq > TC_LQ:
+    if precision == "fp32" or d != TC_DIM or lq > TC_LQ_MAX or (needs_grad and lq > TC_LQ):
         return maxsim_exact(Q, P, qmask, pmask)
     if precision == "bf16x3" and not needs_grad:
         # high-fidelity tensor-core mode for operands that are not bf16-representable
         with torch.no_grad():
-            Qb, qm32 = pack_queries(Q, qmask, 3)
-            return PackedPages.from_padded(P.detach(), pmask, k_blocks=3).score_packed(Qb, qm32)
+            return PackedPages.from_padded(P.detach(), pmask, k_blocks=3).score(Q.detach(), qmask)
     if needs_grad:
         # training: tensor-core search + fp32 rescoring of the winners, backward through the same indices
         return _MaxSimRescoreFn.apply(_float_operand(Q), _float_operand(P), _mask_u8(qmask), _mask_u8(pmask))
     with torch.no_grad():
-        Qb, qm32 = pack_queries(Q, qmask)
-        return _packed_for(P.detach(), pmask).score_packed(Qb, qm32)
+        return _packed_for(P.detach(), pmask).score(Q.detach(), qmask)   # lq > 32: scored as 32-token groups
 
 
 # ---------------------------------------------------------------------------
@@ -333,9 +331,8 @@ class BaseVisualRetrieverProcessor(ABC):
             P[j, : lens[j]] = p.to(device=device, dtype=torch.float32)
             pm[j, : lens[j] + (1 if padded[j] else 0)] = True   # the extra valid slot is a zero token
         with torch.no_grad():
-            if d == TC_DIM and lq <= TC_LQ and os.environ.get("EVDR_PRECISION", "bf16") != "fp32":
-                Qb, qm32 = pack_queries(Q, qm)
-                scores = PackedPages.from_padded(P, pm, varlen=True).score_packed(Qb, qm32)
+            if d == TC_DIM and lq <= TC_LQ_MAX and os.environ.get("EVDR_PRECISION", "bf16") != "fp32":
+                scores = PackedPages.from_padded(P, pm, varlen=True).score(Q, qm)
             else:
                 scores = maxsim_exact(Q, P, qm, pm)
         scores = scores.cpu()

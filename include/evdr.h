@@ -151,6 +151,12 @@ EVDR_API int evdr_maxsim_packed_fwd(evdr_handle* h,
                                     int64_t total_chunks, int pages_per_item, int k_blocks,
                                     float* out_dev, int64_t out_ld, void* stream);
 
+/* Queries longer than 32 tokens on the tensor-core path: the host splits a query into `groups`
+ * 32-token groups scored as separate rows (exact: the max over page tokens is per query token);
+ * evdr_group_sum adds the group rows back: out[q, c] = sum_g in[q*groups + g, c]. */
+EVDR_API int evdr_group_sum(evdr_handle* h, const float* in_dev, int64_t in_ld, int nq, int groups,
+                            int np, float* out_dev, int64_t out_ld, void* stream);
+
 /* Gradient calls: tensor-core search + fp32 rescoring.
  * evdr_maxsim_packed_argmax runs the same tcgen05 kernel but emits, instead of scores, the packed
  *   slot attaining each max: argmax_slots_dev int32, PAGE-MAJOR [np, nq*lq] (position inside the

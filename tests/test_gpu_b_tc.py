@@ -152,3 +152,14 @@ def test_search_api(evdr, cuda):
     s, ids = pk.search(Q, qm, k=10)
     assert (ids[:, 0] == rel + 5000).all()
     assert (s[:, :-1] >= s[:, 1:]).all()
+
+
+@pytest.mark.parametrize("lq", [33, 50, 64, 100, 128])
+def test_long_queries_split_into_groups(evdr, cuda, lq):
+    """Queries of up to 128 tokens stay on the tensor-core path as 32-token groups (exact split)."""
+    P, pm = evdr.synth.make_pages(120, 333, seed=lq, device=cuda, n_holes=4, empty_frac=0.02, min_len=50)
+    Q, qm, rel = evdr.synth.make_queries(P, pm, 11, lq, seed=lq + 1, sigma=2.0, min_len=lq // 2, drop=0.1)
+    got = evdr.score_multi_vector_masked(Q, P, qm, pm)
+    ref = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
+    U.assert_scores_close(got.cpu().numpy(), ref.cpu().numpy())
+    assert got.shape == (11, 120)
