@@ -36,6 +36,8 @@ _SIGNATURES = {
     "evdr_maxsim_bwd": ([_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "evdr_pack_plan": ([_vp, _vp, _i, _i, _i, _vp, _vp], _i),
     "evdr_pack_pages": ([_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "evdr_pack_plan_ragged": ([_vp, _vp, _vp, _i, _vp, _vp], _i),
+    "evdr_pack_pages_ragged": ([_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "evdr_pack_queries": ([_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "evdr_maxsim_packed_fwd": ([_vp, _vp, _vp, _i, _vp, _i64, _vp, _i, _i64, _i, _i, _vp, _i64, _vp], _i),
     "evdr_maxsim_packed_argmax": ([_vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp], _i),

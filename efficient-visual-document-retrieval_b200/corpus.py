@@ -128,6 +128,58 @@ class PackedPages:
         return PackedPages(tokens, chunk_off, npg, total, page_offset, k_blocks)
 
     @staticmethod
+    def from_object_arrays(documents, doc_attnmask=None, doc_imgmask=None, *, device, normalize: bool = False,
+                           page_offset: int = 0, k_blocks: int = 1) -> "PackedPages":
+        """Pack the reference's on-disk layout directly: ``documents`` is a sequence (numpy object array /
+        list) of (Li, 128) float arrays, the masks sequences of (Li,) bool-like arrays or None -- the
+        arguments of utils/preprocess_data.py:80-105 (preprocess_docs).  The page mask is
+        valid & attn & img like :101.  Tokens are concatenated once on the host, copied once, and packed
+        on the device (evdr_pack_*_ragged); no padded (N, Lmax, D) fp32 tensor is built."""
+        import numpy as np
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.EvdrError("from_object_arrays packs on the GPU: this package has no CPU fallback")
+        docs = [np.asarray(x, dtype=np.float32).reshape(-1, TC_DIM) for x in documents]
+        npg = len(docs)
+        lens = np.array([x.shape[0] for x in docs], dtype=np.int64)
+        off = np.zeros(npg + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        total_tok = int(off[-1])
+        flat = np.concatenate(docs, axis=0) if total_tok else np.zeros((0, TC_DIM), np.float32)
+        mask = np.ones(total_tok, dtype=bool)
+        for src in (doc_attnmask, doc_imgmask):
+            if src is None:
+                continue
+            for i in range(npg):
+                mi = src[i]
+                if mi is None:
+                    continue
+                mi = np.asarray(mi).astype(bool).reshape(-1)
+                L = min(int(lens[i]), mi.shape[0])
+                seg = mask[off[i]:off[i + 1]]
+                seg[:L] &= mi[:L]
+                seg[L:] = False                    # mask shorter than the page: padded False (:75-76)
+        tok_d = torch.from_numpy(flat).to(device, non_blocking=True)
+        mask_d = torch.from_numpy(mask.view(np.uint8)).to(device, non_blocking=True)
+        off_d = torch.from_numpy(off).to(device, non_blocking=True)
+        if total_tok == 0:
+            tok_d = torch.zeros((1, TC_DIM), dtype=torch.float32, device=device)
+            mask_d = torch.zeros(1, dtype=torch.uint8, device=device)
+        lib = _lib.load()
+        h = _lib.handle(device)
+        st = _lib.stream_ptr(device)
+        chunk_off = torch.empty(npg + 1, dtype=torch.int32, device=device)
+        _lib.check(lib.evdr_pack_plan_ragged(h, mask_d.data_ptr(), off_d.data_ptr(), npg, chunk_off.data_ptr(), st),
+                   "evdr_pack_plan_ragged")
+        total = int(chunk_off[-1].item())
+        tokens = torch.empty((total * CHUNK, TC_DIM * k_blocks), dtype=torch.bfloat16, device=device)
+        _lib.check(lib.evdr_pack_pages_ragged(h, tok_d.data_ptr(), _lib.EVDR_F32, mask_d.data_ptr(), off_d.data_ptr(),
+                                              chunk_off.data_ptr(), npg, max(1, int(lens.max()) if npg else 1),
+                                              TC_DIM, 1 if normalize else 0, k_blocks, tokens.data_ptr(), st),
+                   "evdr_pack_pages_ragged")
+        return PackedPages(tokens, chunk_off, npg, total, page_offset, k_blocks)
+
+    @staticmethod
     def from_uniform_tokens(tokens: torch.Tensor, page_offset: int = 0) -> "PackedPages":
         """Zero-copy view of an all-valid bf16 corpus (np, L, 128) with L % 16 == 0."""
         _lib.require_cuda(tokens, "tokens")

@@ -30,18 +30,21 @@ __device__ __forceinline__ float4 residual_bf16x4(float4 v, uint2 hi) {
 
 // n_chunks[c]; varlen: ceil((last valid + 1)/16), min 1; else ceil(lp/16)
 __global__ void __launch_bounds__(256)
-plan_len_kernel(const uint8_t* __restrict__ pmask, int np, int lp, int varlen,
-                int32_t* __restrict__ nch) {
+plan_len_kernel(const uint8_t* __restrict__ pmask, const long long* __restrict__ in_off, int np, int lp,
+                int varlen, int32_t* __restrict__ nch) {
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= np) return;
+  // ragged input (in_off != null): page c owns tokens in_off[c] .. in_off[c+1] of a flat array
+  const long long base = in_off ? in_off[c] : (long long)c * lp;
+  if (in_off) lp = (int)(in_off[c + 1] - base);
   int n;
   if (!varlen) {
     n = (lp + CH - 1) / CH;
   } else {
     int last = -1;
     for (int m = lane; m < lp; m += 32)
-      if (pmask[(size_t)c * lp + m]) last = m;
+      if (pmask[base + m]) last = m;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
     n = (last + 1 + CH - 1) / CH;
@@ -95,8 +98,8 @@ plan_scan_kernel(const int32_t* __restrict__ nch, int np, int32_t* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
-                  const int32_t* __restrict__ chunk_off, int np, int lp, int normalize, int kb,
-                  __nv_bfloat16* __restrict__ tokens) {
+                  const long long* __restrict__ in_off, const int32_t* __restrict__ chunk_off, int np,
+                  int lp, int normalize, int kb, __nv_bfloat16* __restrict__ tokens) {
   extern __shared__ int src[];  // n_slots ints
   __shared__ int seg_last[256];
   __shared__ int first_valid_s;
@@ -104,7 +107,9 @@ pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
   const int c = blockIdx.x;
   const int c0 = chunk_off[c];
   const int n_slots = (chunk_off[c + 1] - c0) * CH;
-  const uint8_t* mc = pmask + (size_t)c * lp;
+  const long long base = in_off ? in_off[c] : (long long)c * lp;   // ragged input: flat token array
+  if (in_off) lp = (int)(in_off[c + 1] - base);
+  const uint8_t* mc = pmask + base;
 
   // segmented "last valid index" scan: thread t owns slots [t*seg, (t+1)*seg)
   const int seg = (n_slots + 255) / 256;
@@ -140,7 +145,7 @@ pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
 
   const int row = EVDR_TC_DIM * kb;        // kb = 3: [hi | lo | hi] rows of the bf16x3 split
   __nv_bfloat16* dst = tokens + (size_t)c0 * CH * row;
-  const T* Pc = P + (size_t)c * lp * EVDR_TC_DIM;
+  const T* Pc = P + base * EVDR_TC_DIM;
   for (int m = warp; m < n_slots; m += (blockDim.x >> 5)) {
     const int s = src[m];
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -269,15 +274,15 @@ using namespace evdr;
 
 extern "C" {
 
-int evdr_pack_plan(evdr_handle* h, const uint8_t* pmask, int np, int lp, int varlen,
-                   int32_t* chunk_off, void* stream) {
+static int pack_plan_impl(evdr_handle* h, const uint8_t* pmask, const long long* in_off, int np, int lp,
+                          int varlen, int32_t* chunk_off, void* stream) {
   EVDR_REQUIRE_HANDLE(h);
   EVDR_CHECK_ARG(chunk_off && np >= 1 && lp >= 1, "evdr_pack_plan: bad arguments");
   EVDR_CHECK_ARG(!varlen || pmask, "evdr_pack_plan: varlen needs pmask");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* nch = nullptr;
   EVDR_CUDA(cudaMallocAsync(&nch, sizeof(int32_t) * (size_t)np, st));
-  plan_len_kernel<<<(np + 7) / 8, 256, 0, st>>>(pmask, np, lp, varlen, nch);
+  plan_len_kernel<<<(np + 7) / 8, 256, 0, st>>>(pmask, in_off, np, lp, varlen, nch);
   EVDR_LAUNCH_CHECK("plan_len_kernel");
   plan_scan_kernel<<<1, 1024, 0, st>>>(nch, np, chunk_off);
   EVDR_LAUNCH_CHECK("plan_scan_kernel");
@@ -285,9 +290,20 @@ int evdr_pack_plan(evdr_handle* h, const uint8_t* pmask, int np, int lp, int var
   return EVDR_OK;
 }
 
-int evdr_pack_pages(evdr_handle* h, const void* P, int p_dtype, const uint8_t* pmask,
-                    const int32_t* chunk_off, int np, int lp, int d, int normalize, int k_blocks,
-                    void* tokens, void* stream) {
+int evdr_pack_plan(evdr_handle* h, const uint8_t* pmask, int np, int lp, int varlen,
+                   int32_t* chunk_off, void* stream) {
+  return pack_plan_impl(h, pmask, nullptr, np, lp, varlen, chunk_off, stream);
+}
+
+int evdr_pack_plan_ragged(evdr_handle* h, const uint8_t* mask_flat, const int64_t* tok_off, int np,
+                          int32_t* chunk_off, void* stream) {
+  if (!mask_flat || !tok_off) return set_error(EVDR_ERR_INVALID, "evdr_pack_plan_ragged: null pointer");
+  return pack_plan_impl(h, mask_flat, reinterpret_cast<const long long*>(tok_off), np, 1, 1, chunk_off, stream);
+}
+
+static int pack_pages_impl(evdr_handle* h, const void* P, int p_dtype, const uint8_t* pmask,
+                           const long long* in_off, const int32_t* chunk_off, int np, int lp, int d,
+                           int normalize, int k_blocks, void* tokens, void* stream) {
   EVDR_REQUIRE_HANDLE(h);
   EVDR_CHECK_ARG(P && pmask && chunk_off && tokens, "evdr_pack_pages: null pointer");
   EVDR_CHECK_ARG(d == EVDR_TC_DIM, "evdr_pack_pages: d=%d, the tensor-core path needs d=128", d);
@@ -300,18 +316,32 @@ int evdr_pack_pages(evdr_handle* h, const void* P, int p_dtype, const uint8_t* p
     return set_error(EVDR_ERR_UNSUPPORTED, "evdr_pack_pages: lp=%d too long", lp);
   if (p_dtype == EVDR_F32) {
     EVDR_CUDA(cudaFuncSetAttribute(pack_pages_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pack_pages_kernel<float><<<np, 256, smem, st>>>(static_cast<const float*>(P), pmask, chunk_off, np,
+    pack_pages_kernel<float><<<np, 256, smem, st>>>(static_cast<const float*>(P), pmask, in_off, chunk_off, np,
                                                    lp, normalize, k_blocks, static_cast<__nv_bfloat16*>(tokens));
   } else if (p_dtype == EVDR_BF16) {
     EVDR_CUDA(cudaFuncSetAttribute(pack_pages_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pack_pages_kernel<__nv_bfloat16><<<np, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(P), pmask,
-                                                           chunk_off, np, lp, normalize, k_blocks,
+                                                           in_off, chunk_off, np, lp, normalize, k_blocks,
                                                            static_cast<__nv_bfloat16*>(tokens));
   } else {
     return set_error(EVDR_ERR_INVALID, "evdr_pack_pages: bad dtype %d", p_dtype);
   }
   EVDR_LAUNCH_CHECK("pack_pages_kernel");
   return EVDR_OK;
+}
+
+int evdr_pack_pages(evdr_handle* h, const void* P, int p_dtype, const uint8_t* pmask,
+                    const int32_t* chunk_off, int np, int lp, int d, int normalize, int k_blocks,
+                    void* tokens, void* stream) {
+  return pack_pages_impl(h, P, p_dtype, pmask, nullptr, chunk_off, np, lp, d, normalize, k_blocks, tokens, stream);
+}
+
+int evdr_pack_pages_ragged(evdr_handle* h, const void* tok_flat, int dtype, const uint8_t* mask_flat,
+                           const int64_t* tok_off, const int32_t* chunk_off, int np, int max_len, int d,
+                           int normalize, int k_blocks, void* tokens, void* stream) {
+  if (!tok_off) return set_error(EVDR_ERR_INVALID, "evdr_pack_pages_ragged: null tok_off");
+  return pack_pages_impl(h, tok_flat, dtype, mask_flat, reinterpret_cast<const long long*>(tok_off), chunk_off,
+                         np, max_len, d, normalize, k_blocks, tokens, stream);
 }
 
 int evdr_pack_queries(evdr_handle* h, const void* Q, int q_dtype, const uint8_t* qmask, int nq,

@@ -127,6 +127,16 @@ EVDR_API int evdr_pack_pages(evdr_handle* h, const void* P_dev, int p_dtype,
                              const uint8_t* pmask_dev, const int32_t* chunk_off_dev,
                              int np, int lp, int d, int normalize, int k_blocks,
                              void* tokens_bf16_dev, void* stream);
+/* Ragged input (the on-disk layout: object arrays of (Li, 128) tokens with attention / image masks,
+ * utils/preprocess_data.py:37-105, schema preprocess/split_data.py:29-36): one flat token array
+ * [T, 128] + flat uint8 mask [T] (valid & attn & img) + int64 tok_off[np+1]; no padded (N, Lmax, D)
+ * intermediate is ever built.  The plan is always varlen; max_len = longest page (sizes scratch). */
+EVDR_API int evdr_pack_plan_ragged(evdr_handle* h, const uint8_t* mask_flat_dev, const int64_t* tok_off_dev,
+                                   int np, int32_t* chunk_off_dev, void* stream);
+EVDR_API int evdr_pack_pages_ragged(evdr_handle* h, const void* tok_flat_dev, int dtype,
+                                    const uint8_t* mask_flat_dev, const int64_t* tok_off_dev,
+                                    const int32_t* chunk_off_dev, int np, int max_len, int d,
+                                    int normalize, int k_blocks, void* tokens_bf16_dev, void* stream);
 /* Queries for the tensor-core path: bf16 [nq, 32, 128], masked / padded token
  * slots zeroed; qmask32 [nq, 32] uint8.  Requires lq <= 32, d == 128. */
 EVDR_API int evdr_pack_queries(evdr_handle* h, const void* Q_dev, int q_dtype,

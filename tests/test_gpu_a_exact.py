@@ -321,3 +321,45 @@ def test_evaluate_scores_fast_path(evdr, cuda):
     got = ev.evaluate_scores(dense.to(cuda), torch.tensor(off), torch.tensor(ids), torch.tensor(rels), tie_rank=tie.to(cuda))
     want = ev.compute_mteb_metrics(qrels, results)
     assert got == want
+
+
+def test_from_object_arrays_matches_padded_pipeline(evdr, cuda):
+    """The on-disk layout (object arrays of (Li,128) + attention / image masks) packed directly equals
+    the reference's route: zero-pad to (N, Lmax, 128), mask = valid & attn & img
+    (utils/preprocess_data.py:80-105), then pack."""
+    rng = np.random.default_rng(0)
+    lens = [37, 1, 200, 64, 16, 129, 5]
+    docs = np.empty(len(lens), dtype=object)
+    attn = np.empty(len(lens), dtype=object)
+    img = np.empty(len(lens), dtype=object)
+    for i, L in enumerate(lens):
+        x = rng.standard_normal((L, 128)).astype(np.float32)
+        docs[i] = x / np.linalg.norm(x, axis=-1, keepdims=True)
+        attn[i] = rng.random(L) > 0.1
+        img[i] = (rng.random(L) > 0.2).astype(np.int64)
+    attn[3] = attn[3][:40]            # a mask shorter than its page: the rest is padded False
+    img[4] = np.zeros(16, dtype=bool)  # a page with no valid token
+    pk = evdr.PackedPages.from_object_arrays(docs, attn, img, device=cuda)
+    # reference route restated with numpy (pad_tokens_object / pad_mask_object)
+    Lmax = max(lens)
+    P = np.zeros((len(lens), Lmax, 128), np.float32)
+    valid = np.zeros((len(lens), Lmax), bool)
+    am = np.zeros_like(valid)
+    im = np.zeros_like(valid)
+    for i, L in enumerate(lens):
+        P[i, :L] = docs[i]
+        valid[i, :L] = True
+        a = np.asarray(attn[i]).astype(bool)
+        am[i, :min(Lmax, a.shape[0])] = a[:Lmax]
+        b = np.asarray(img[i]).astype(bool)
+        im[i, :min(Lmax, b.shape[0])] = b[:Lmax]
+    pm = valid & am & im
+    ref = evdr.PackedPages.from_padded(torch.from_numpy(P).to(cuda), torch.from_numpy(pm).to(cuda), varlen=True)
+    assert torch.equal(pk.chunk_off, ref.chunk_off) and pk.total_chunks == ref.total_chunks
+    assert torch.equal(pk.tokens, ref.tokens)
+    Q = torch.nn.functional.normalize(torch.randn(6, 20, 128, generator=torch.Generator().manual_seed(1)), dim=-1).to(cuda)
+    qm = torch.ones(6, 20, dtype=torch.bool, device=cuda)
+    want = mo.maxsim_masked(Q.cpu().numpy(), P, qm.cpu().numpy(), pm)
+    U.assert_scores_close(pk.score(Q, qm).cpu().numpy(), want, rel=2e-3)   # operands not bf16-representable
+    pk3 = evdr.PackedPages.from_object_arrays(docs, attn, img, device=cuda, k_blocks=3)
+    U.assert_scores_close(pk3.score(Q, qm).cpu().numpy(), want, rel=1e-5)
