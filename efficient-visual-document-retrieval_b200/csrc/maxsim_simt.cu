@@ -315,6 +315,57 @@ static int launch_rescore(const void* Q, const void* P, const uint8_t* pmask, in
   return EVDR_OK;
 }
 
+// Hard-token mining (mainv3_iter_liscore_QA_hardtoken.py:398-425): for a (query, page) pair the page
+// token m maximising  max_{valid n} <Q[q,n], P[c,m]>  over the VALID page tokens (the column-max
+// variant of MaxSim; masked page tokens are -inf, ties -> lowest index like torch.argmax).
+// One CTA per pair: the query's tokens sit in shared memory, each warp walks page tokens.
+template <typename TQ, typename TP>
+__global__ void __launch_bounds__(256)
+hard_token_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P, const uint8_t* __restrict__ qmask,
+                  const uint8_t* __restrict__ pmask, const long long* __restrict__ doc_idx, int A, int lq,
+                  int lp, int d, long long* __restrict__ out_idx) {
+  extern __shared__ float qs[];                 // lq * d
+  __shared__ float wbest[8];
+  __shared__ int widx[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.x / A;
+  const long long c = doc_idx[blockIdx.x];
+  for (int i = tid; i < lq * d; i += blockDim.x) qs[i] = to_f32(Q[(size_t)q * lq * d + i]);
+  __syncthreads();
+  const uint8_t* qm = qmask + (size_t)q * lq;
+  const uint8_t* pm = pmask + (size_t)c * lp;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int m = warp; m < lp; m += 8) {
+    if (!pm[m]) continue;                       // sim[:, ~doc_mask] = -inf
+    const TP* p = P + ((size_t)c * lp + m) * d;
+    float colmax = -INFINITY;
+    for (int n = 0; n < lq; ++n) {
+      if (!qm[n]) continue;                     // q_tokens[q_mask]
+      float acc = 0.f;
+      for (int i = lane * 4; i < d; i += 128) {
+        const float4 b = load4(p + i);
+        const float* a = qs + n * d + i;
+        acc = fmaf(a[0], b.x, acc);
+        acc = fmaf(a[1], b.y, acc);
+        acc = fmaf(a[2], b.z, acc);
+        acc = fmaf(a[3], b.w, acc);
+      }
+      colmax = fmaxf(colmax, warp_sum(acc));
+    }
+    if (colmax > best) { best = colmax; bidx = m; }   // ascending m per warp: first index kept
+  }
+  if (lane == 0) { wbest[warp] = best; widx[warp] = bidx; }
+  __syncthreads();
+  if (tid == 0) {
+    float v = wbest[0];
+    int ix = widx[0];
+    for (int w = 1; w < 8; ++w)
+      if (wbest[w] > v || (wbest[w] == v && widx[w] < ix)) { v = wbest[w]; ix = widx[w]; }
+    out_idx[blockIdx.x] = (ix == 0x7fffffff) ? 0 : ix;  // no valid page token: torch.argmax of all -inf is 0
+  }
+}
+
 __global__ void has_page_kernel(const uint8_t* __restrict__ pmask, int np, int lp,
                                 uint8_t* __restrict__ has) {
   const int lane = threadIdx.x & 31;
@@ -366,6 +417,35 @@ int evdr_maxsim_fwd(evdr_handle* h, const void* Q, int q_dtype, const void* P, i
   if (rc != EVDR_OK) return rc;
   rowsum_kernel<<<(np + 7) / 8, 256, 0, st>>>(rowmax_ws, qmask, pmask, nq, np, lq, lp, out);
   EVDR_LAUNCH_CHECK("rowsum_kernel");
+  return EVDR_OK;
+}
+
+int evdr_hard_token_argmax(evdr_handle* h, const void* Q, int q_dtype, const void* P, int p_dtype,
+                           const uint8_t* qmask, const uint8_t* pmask, const int64_t* doc_idx, int nq,
+                           int n_docs_per_query, int lq, int lp, int d, int64_t* out_idx, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(Q && P && qmask && pmask && doc_idx && out_idx, "evdr_hard_token_argmax: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && n_docs_per_query >= 1 && lq >= 1 && lp >= 1 && d >= 4 && d % 4 == 0,
+                 "evdr_hard_token_argmax: bad shape");
+  const size_t smem = sizeof(float) * (size_t)lq * d;
+  if (smem > h->smem_optin) return set_error(EVDR_ERR_UNSUPPORTED, "evdr_hard_token_argmax: lq*d too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)nq * (unsigned)n_docs_per_query;
+  const long long* di = reinterpret_cast<const long long*>(doc_idx);
+  long long* oi = reinterpret_cast<long long*>(out_idx);
+#define EVDR_HT(TQ, TP)                                                                              \
+  do {                                                                                               \
+    EVDR_CUDA(cudaFuncSetAttribute(hard_token_kernel<TQ, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    hard_token_kernel<TQ, TP><<<grid, 256, smem, st>>>(static_cast<const TQ*>(Q), static_cast<const TP*>(P), qmask, \
+                                                        pmask, di, n_docs_per_query, lq, lp, d, oi);  \
+  } while (0)
+  if (q_dtype == EVDR_F32 && p_dtype == EVDR_F32) EVDR_HT(float, float);
+  else if (q_dtype == EVDR_F32 && p_dtype == EVDR_BF16) EVDR_HT(float, __nv_bfloat16);
+  else if (q_dtype == EVDR_BF16 && p_dtype == EVDR_F32) EVDR_HT(__nv_bfloat16, float);
+  else if (q_dtype == EVDR_BF16 && p_dtype == EVDR_BF16) EVDR_HT(__nv_bfloat16, __nv_bfloat16);
+  else return set_error(EVDR_ERR_INVALID, "evdr_hard_token_argmax: dtype must be EVDR_F32 or EVDR_BF16");
+#undef EVDR_HT
+  EVDR_LAUNCH_CHECK("hard_token_kernel");
   return EVDR_OK;
 }
 

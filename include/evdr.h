@@ -187,6 +187,15 @@ EVDR_API int evdr_maxsim_rescore(evdr_handle* h,
                                  int32_t* argmax_dev, int nq, int np, int lq, int lp, int d,
                                  float* rowmax_ws_dev, float* out_dev, void* stream);
 
+/* A8  hard-token mining (mainv3_iter_liscore_QA_hardtoken.py:398-425): for every (query q, page
+ * doc_idx[q, a]) the index of the VALID page token m maximising max_{valid n} <Q[q,n], P[c,m]> (the
+ * column-max variant of MaxSim; ties -> lowest index).  Replaces a Python double loop with a host
+ * sync per pair.  doc_idx / out_idx: int64 [nq, n_docs_per_query]. */
+EVDR_API int evdr_hard_token_argmax(evdr_handle* h, const void* Q_dev, int q_dtype, const void* P_dev,
+                                    int p_dtype, const uint8_t* qmask_dev, const uint8_t* pmask_dev,
+                                    const int64_t* doc_idx_dev, int nq, int n_docs_per_query, int lq,
+                                    int lp, int d, int64_t* out_idx_dev, void* stream);
+
 /* ------------------------------------------------------------------------
  * A7  evaluation tail: top-k and trec_eval-style measures on device
  * (replaces the Nq*Np `.item()` dict build of mainv2_iter_listwise.py:312-318 and

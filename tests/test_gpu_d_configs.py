@@ -177,3 +177,26 @@ def test_bf16x3_high_fidelity_mode(evdr, cuda, nq, npg, lp):
     e1 = ((bf - exact).abs() / exact.abs().clamp_min(1)).max().item()
     assert e3 < 5e-6, e3
     assert e1 < 1e-3 and e3 < e1
+
+
+def test_hard_token_mining_matches_reference_loop(evdr, cuda):
+    """mainv3_iter_liscore_QA_hardtoken.py:398-425 restated in torch (the per-pair loop) vs one launch."""
+    P, pm = evdr.synth.make_pages(60, 333, seed=3, device=cuda, n_holes=5, empty_frac=0.0, min_len=40)
+    Q, qm, rel = evdr.synth.make_queries(P, pm, 32, 32, seed=4, sigma=2.0, min_len=6, drop=0.1)
+    g = torch.Generator(device=cuda).manual_seed(5)
+    doc_idx = torch.randint(0, 60, (32, 4), generator=g, device=cuda)
+    got = evdr.hard_token_argmax(Q, qm, P, pm, doc_idx)
+    Pf, Qf = P.float(), Q.float()
+    for qi in range(32):
+        qt = Qf[qi][qm[qi]]
+        for a in range(4):
+            dmask = pm[doc_idx[qi, a]]
+            sim = qt @ Pf[doc_idx[qi, a]].T
+            sim[:, ~dmask] = float("-inf")
+            want = torch.argmax(sim.max(dim=0).values)
+            if got[qi, a] != want:   # only an exact-tie / last-bit difference may pick another token
+                col = sim.max(dim=0).values
+                assert abs(col[got[qi, a]] - col[want]) < 1e-6
+    toks = evdr.hard_tokens(Q, qm, P, pm, doc_idx)
+    assert toks.shape == (128, 1, 128)
+    assert torch.equal(toks[5, 0], P[doc_idx.reshape(-1)[5], got.reshape(-1)[5]])
