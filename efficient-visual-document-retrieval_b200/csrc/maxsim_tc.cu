@@ -74,7 +74,10 @@ struct TcCfg {
   static constexpr int TILES_PER_GROUP = CG2 ? 2 * R : R;
 };
 
-template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1>
+// SP ("short pages"): epilogue variant for corpora whose pages are shorter than a tile, where several
+// pages end inside every tile -- page-end work is batched (see `flush`); the default variant keeps the
+// leaner code that is fastest when a page spans several tiles.
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                  const TcParams prm) {
@@ -320,12 +323,25 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         cur_g = g;
       }
       // page-end cache: lane l holds the (item-relative) end chunk of page p0 + 32*cb + l
+      // (the NEXT batch of 32 is loaded as soon as a batch becomes current, so the global-load latency
+      //  is hidden behind 32 pages of work)
       int cb = 0;
       auto load_pe = [&](int b) {
         const int pp = p0 + 32 * b + lane;
         return (pp < p1) ? (prm.chunk_off[pp + 1] - c0) : 0x7fffffff;
       };
       int pe_cache = load_pe(0);
+      int pe_next = SP ? load_pe(1) : 0;
+      auto set_batch = [&](int b) {
+        if constexpr (SP) {
+          if (b == cb + 1) { pe_cache = pe_next; }
+          else { pe_cache = load_pe(b); }
+          pe_next = load_pe(b + 1);
+        } else {
+          pe_cache = load_pe(b);
+        }
+        cb = b;
+      };
       int p = p0;                     // current page
       int pe = __shfl_sync(0xffffffffu, pe_cache, 0);
       float runmax[R];
@@ -347,7 +363,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               p = p_save;
               pstart = pstart_save;
               const int b = (p - p0) >> 5;
-              if (b != cb) { cb = b; pe_cache = load_pe(b); }
+              if (b != cb) set_batch(b);
               pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
             }
             const int buf = acc_it & 1;
@@ -357,6 +373,24 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             float rm = runmax[r];
             int bc = best_chunk[r], bp = best_pos[r];
             // page complete for this query tile: mask, reduce the 32 query tokens, store, next page
+            // Completed pages are queued (up to 4 per flush): their 32-token sums are reduced with
+            // interleaved shuffles and written by 4 lanes in one store, instead of one serial
+            // shuffle chain + store per page (short compressed pages end 4 or more times per tile).
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+            int nfin = 0, fin_page0 = 0;
+            auto flush = [&]() {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+                f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+                f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+                f3 += __shfl_xor_sync(0xffffffffu, f3, o);
+              }
+              const float v = lane == 0 ? f0 : lane == 1 ? f1 : lane == 2 ? f2 : f3;
+              if (lane < nfin && qidx[r] >= 0)
+                prm.out[(size_t)qidx[r] * prm.out_ld + fin_page0 + lane] = v;
+              nfin = 0;
+            };
             auto finalize = [&]() {
               if constexpr (AM) {
                 // winning packed slot of this (query token, page): chunk within the page * 16 + position
@@ -365,6 +399,14 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                   prm.argmax[(size_t)p * ((size_t)prm.nq * prm.lq) + (size_t)qidx[r] * prm.lq + lane] = slot;
                 pstart = pe;
                 bc = pe;
+              } else if constexpr (SP) {
+                const float v = rm * qm[r];
+                if (nfin == 0) fin_page0 = p;
+                f0 = nfin == 0 ? v : f0;
+                f1 = nfin == 1 ? v : f1;
+                f2 = nfin == 2 ? v : f2;
+                f3 = nfin == 3 ? v : f3;
+                if (++nfin == 4) flush();
               } else {
                 const float s = warp_sum(rm * qm[r]);
                 if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
@@ -372,7 +414,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               rm = -INFINITY;
               ++p;
               const int b = (p - p0) >> 5;
-              if (b != cb) { cb = b; pe_cache = load_pe(b); }
+              if (b != cb) set_batch(b);
               pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
             };
             // ---- drain: per-chunk (16-column) maxes of this tile into registers.  TMEM loads are
@@ -409,10 +451,14 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             // ---- fold the chunk maxes into the running per-page max; a page can end after any chunk
             const bool whole_tile = !AM && (pe >= ch_tile0 + CH_PER_TILE);
             if (whole_tile) {
-              float m = rm;
+              if constexpr (SP && CH_PER_TILE == 16) {
+                rm = max_tree16r(rm, h);
+              } else {
+                float m = rm;
 #pragma unroll
-              for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, h[j], h[j + 1]);
-              rm = m;
+                for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, h[j], h[j + 1]);
+                rm = m;
+              }
               if (pe == ch_tile0 + CH_PER_TILE) finalize();
             } else {
               // compact (not unrolled) segment loop: ONE copy of finalize per resident tile keeps the
@@ -422,22 +468,38 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
 #pragma unroll 1
               while (lo < CH_PER_TILE) {
                 const int hi = min(pe - ch_tile0, CH_PER_TILE);   // pe is INT_MAX past the item's end
+                if constexpr (AM) {
 #pragma unroll
-                for (int j = 0; j < CH_PER_TILE; ++j) {
-                  if constexpr (AM) {
+                  for (int j = 0; j < CH_PER_TILE; ++j) {
                     // strict '>' in ascending chunk order keeps the first chunk attaining the max
                     const bool take = (j >= lo && j < hi) && (h[j] > rm);
                     rm = take ? h[j] : rm;
                     bc = take ? ch_tile0 + j : bc;
                     bp = take ? hp[j] : bp;
-                  } else {
+                  }
+                } else if constexpr (!SP) {
+#pragma unroll
+                  for (int j = 0; j < CH_PER_TILE; ++j)
                     rm = (j >= lo && j < hi) ? fmaxf(rm, h[j]) : rm;
+                } else {
+                  // masked tree: one op on the rm chain per segment instead of one per chunk
+                  float g[CH_PER_TILE];
+#pragma unroll
+                  for (int j = 0; j < CH_PER_TILE; ++j) g[j] = (j >= lo && j < hi) ? h[j] : -INFINITY;
+                  if constexpr (CH_PER_TILE == 16) {
+                    rm = max_tree16r(rm, g);
+                  } else {
+                    float m = rm;
+#pragma unroll
+                    for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, g[j], g[j + 1]);
+                    rm = m;
                   }
                 }
                 if (pe - ch_tile0 <= CH_PER_TILE) finalize();
                 lo = hi;
               }
             }
+            if constexpr (!AM && SP) { if (nfin > 0) flush(); }
             runmax[r] = rm;
             best_chunk[r] = bc;
             best_pos[r] = bp;
@@ -474,7 +536,7 @@ static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uin
   return EVDR_OK;
 }
 
-template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1>
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false>
 static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens,
                      TcParams prm, cudaStream_t st) {
   using S = TcCfg<R, BN, STAGES, CG2, KB>;
@@ -483,7 +545,7 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   if (rc != EVDR_OK) return rc;
   rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, KB, "page tokens");
   if (rc != EVDR_OK) return rc;
-  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB>;
+  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP>;
   if ((size_t)S::TOTAL > h->smem_optin)
     return set_error(EVDR_ERR_UNSUPPORTED, "tensor-core kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -597,6 +659,9 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     if (R == 3) return launch_tc<3, 256, 4, true>(h, Qb, tokens, n_tokens, prm, st);
     return launch_tc<4, 256, 3, true>(h, Qb, tokens, n_tokens, prm, st);
   }
+  // pages shorter than half a tile: several page ends per tile -> batched page-end epilogue
+  const bool short_pages = (double)total_chunks / (double)np < 8.0;
+  if (short_pages && R == 3) return launch_tc<3, 256, 2, false, false, 1, true>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 1) return launch_tc<1, 256, 3, false>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 2) return launch_tc<2, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
   return launch_tc<3, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);

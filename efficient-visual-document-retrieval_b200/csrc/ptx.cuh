@@ -263,6 +263,15 @@ __device__ __forceinline__ float max16(const float (&v)[32], int o) {
   const float a4 = max3(v[o + 12], v[o + 13], v[o + 14]);
   return fmaxf(max3(a0, a1, a2), max3(a3, a4, v[o + 15]));
 }
+// max(rm, x[0..15]) as a depth-3 tree of 3-input maxes (8 FMNMX3)
+__device__ __forceinline__ float max_tree16r(float rm, const float (&x)[16]) {
+  const float t0 = max3(x[0], x[1], x[2]);
+  const float t1 = max3(x[3], x[4], x[5]);
+  const float t2 = max3(x[6], x[7], x[8]);
+  const float t3 = max3(x[9], x[10], x[11]);
+  const float t4 = max3(x[12], x[13], x[14]);
+  return max3(rm, max3(t0, t1, t2), max3(t3, t4, x[15]));
+}
 // first position i in [0,16) with v[o+i] == m (m is the exact max of those 16 values)
 __device__ __forceinline__ int first_pos16(const float (&v)[32], int o, float m) {
   int pos = 15;

@@ -8,10 +8,13 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import evdr_b200 as evdr
 
+import os
 pages = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 nqs = [int(x) for x in sys.argv[2:]] or [1, 4, 8, 12, 64, 256, 1024]
 dev = torch.device("cuda", 0)
-corpus = evdr.synth.make_uniform_corpus(pages, 1040, device=dev, seed=1)
+TOK = int(os.environ.get("TC_BENCH_TOKENS", "1040"))     # token slots per page (64 = compressed pages)
+VALID = 1030 if TOK == 1040 else TOK
+corpus = evdr.synth.make_uniform_corpus(pages, TOK, device=dev, seed=1)
 pk = evdr.PackedPages.from_uniform_tokens(corpus)
 for nq in nqs:
     Q = torch.nn.functional.normalize(torch.randn(nq, 32, 128, device=dev), dim=-1)
@@ -30,5 +33,5 @@ for nq in nqs:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     pairs = nq * pages / (ms * 1e-3)
-    print(f"nq={nq:5d} pages={pages}: {ms:9.3f} ms  {pairs/1e6:9.2f} Mpairs/s  "
-          f"{pairs*2*128*32*1030/1e12:8.1f} TFLOP/s(alg)  {pages*1030*256/(ms*1e-3)/1e9:8.1f} GB/s(alg)", flush=True)
+    print(f"nq={nq:5d} pages={pages} x {TOK} tok: {ms:9.3f} ms  {pairs/1e6:9.2f} Mpairs/s  "
+          f"{pairs*2*128*32*VALID/1e12:8.1f} TFLOP/s(alg)  {pages*VALID*256/(ms*1e-3)/1e9:8.1f} GB/s(alg)", flush=True)
