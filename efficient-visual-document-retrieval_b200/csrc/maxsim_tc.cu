@@ -34,7 +34,6 @@ namespace evdr {
 
 using namespace ptx;
 
-constexpr int TC_THREADS = 192;
 constexpr int A_HALF_BYTES = 128 * 64 * 2;       // one 64-wide K sub-tile (128 rows of 128 B)
 
 struct TcParams {
@@ -77,8 +76,11 @@ struct TcCfg {
 // SP ("short pages"): epilogue variant for corpora whose pages are shorter than a tile, where several
 // pages end inside every tile -- page-end work is batched (see `flush`); the default variant keeps the
 // leaner code that is fastest when a page spans several tiles.
-template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// EW = number of epilogue warps: 4 (one group, TMEM buffers alternate per pass) or 8 (two groups of 4;
+// requires R == 2: pass (tile t, query tile r) always uses TMEM buffer r and is drained by group r, so
+// each group owns one query tile's running state and has two MMA periods per pass).
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                  const TcParams prm) {
   using S = TcCfg<R, BN, STAGES, CG2, KB>;
@@ -88,6 +90,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                             : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
+  static_assert(EW == 4 || (EW == 8 && R == 2 && !CG2), "8 epilogue warps need R == 2, single-CTA");
   constexpr uint32_t IDESC = make_idesc_bf16(CG2 ? 256 : 128, BN);
   constexpr int CH_PER_TILE = BN / EVDR_CHUNK;
 
@@ -127,7 +130,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     // tmem_empty lives in the leader: 4 epilogue warps of each CTA of the pair arrive on it
     for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full(b), 1); mbar_init(bar_t_empty(b), CG2 ? 8 : 4); }
     // scheduler ring: the producer publishes item indices, the MMA thread + 4 epilogue warps consume
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), 5); }
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), 1 + EW); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -220,6 +223,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         if constexpr (CG2) mma_commit_cg2_mc(bar, (uint16_t)0x3); else mma_commit(bar);
       };
       int sslot = 0, sphase = 0;
+      uint32_t use0 = 0, use1 = 0;
       auto next_item = [&](int cur) -> int {
         if constexpr (CG2) {
           return cur < 0 ? unit : cur + n_units;
@@ -249,8 +253,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
           tc_fence_after();
           const uint32_t b_base = sB + stage * S::B_STAGE_BYTES;
           for (int r = 0; r < rc; ++r) {
-            const int buf = acc_it & 1;
-            mbar_wait(bar_t_empty(buf), ((acc_it >> 1) & 1) ^ 1);
+            const int buf = (EW == 8) ? r : (int)(acc_it & 1);
+            const uint32_t nuse = buf ? use1 : use0;          // how often this buffer was filled before
+            mbar_wait(bar_t_empty(buf), (nuse & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * BN;
             const uint32_t a_base = sA + r * A_TILE_BYTES;
@@ -262,6 +267,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               else mma_bf16_ss(d_tmem, da, db, IDESC, k > 0);
             }
             commit(bar_t_full(buf));
+            if (buf) ++use1; else ++use0;
             ++acc_it;
           }
           commit(bar_empty(stage));  // page tile consumed by all resident query tiles
@@ -272,6 +278,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   } else {
     // ===================================================== epilogue warps
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
+    const int egrp = (warp - 2) >> 2;                    // EW == 8: epilogue group 0 / 1 <-> query tile r
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t acc_it = 0;
     int cur_g = -1;
@@ -357,7 +364,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         const int ch_tile0 = t * CH_PER_TILE;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (r < rc) {
+          if (r < rc && (EW == 4 || r == egrp)) {
             // every query tile walks the same chunks of this page tile
             if (p != p_save) {
               p = p_save;
@@ -366,8 +373,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               if (b != cb) set_batch(b);
               pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
             }
-            const int buf = acc_it & 1;
-            mbar_wait(bar_t_full(buf), (acc_it >> 1) & 1);
+            // EW == 4: buffers alternate per pass; EW == 8: this group always drains buffer r
+            const int buf = (EW == 8) ? r : (int)(acc_it & 1);
+            mbar_wait(bar_t_full(buf), (EW == 8) ? (acc_it & 1) : ((acc_it >> 1) & 1));
             tc_fence_after();
             const uint32_t t_addr = t_lane + buf * BN;
             float rm = runmax[r];
@@ -536,7 +544,7 @@ static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uin
   return EVDR_OK;
 }
 
-template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false>
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4>
 static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens,
                      TcParams prm, cudaStream_t st) {
   using S = TcCfg<R, BN, STAGES, CG2, KB>;
@@ -545,7 +553,7 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   if (rc != EVDR_OK) return rc;
   rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, KB, "page tokens");
   if (rc != EVDR_OK) return rc;
-  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP>;
+  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP, EW>;
   if ((size_t)S::TOTAL > h->smem_optin)
     return set_error(EVDR_ERR_UNSUPPORTED, "tensor-core kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -565,7 +573,7 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   } else {
     cfg.gridDim = dim3((unsigned)(n_items < h->sm_count ? n_items : h->sm_count));
   }
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(64 + 32 * EW);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
   prm.sched = nullptr;
@@ -620,6 +628,12 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   else { R = prm.nqt >= 3 ? 3 : prm.nqt; tpg = R; }
   if (argmax) { R = 3; tpg = 3; }   // the argmax variant is instantiated for R = 3 only
   if (k_blocks == 3) { R = 1; tpg = 1; }   // bf16x3: one resident query tile (96 KB), 64-token page tiles
+  // pages shorter than half a tile end several times per tile: the epilogue (not the MMA) is the
+  // limit there -> two epilogue groups, one per resident query tile
+  const bool short_pages = !pair && !argmax && k_blocks == 1 && prm.nqt >= 2 &&
+                           (double)total_chunks / (double)np < 8.0;
+  const bool want_ew8 = mode && strcmp(mode, "ew8") == 0 && !pair && !argmax && k_blocks == 1 && prm.nqt >= 2;
+  if (short_pages || want_ew8) { R = 2; tpg = 2; }
   const int n_qgroups = (prm.nqt + tpg - 1) / tpg;
   const int units = pair ? h->sm_count / 2 : h->sm_count;
   int ppi = pages_per_item;
@@ -659,9 +673,8 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     if (R == 3) return launch_tc<3, 256, 4, true>(h, Qb, tokens, n_tokens, prm, st);
     return launch_tc<4, 256, 3, true>(h, Qb, tokens, n_tokens, prm, st);
   }
-  // pages shorter than half a tile: several page ends per tile -> batched page-end epilogue
-  const bool short_pages = (double)total_chunks / (double)np < 8.0;
-  if (short_pages && R == 3) return launch_tc<3, 256, 2, false, false, 1, true>(h, Qb, tokens, n_tokens, prm, st);
+  if (short_pages) return launch_tc<2, 256, 2, false, false, 1, true, 8>(h, Qb, tokens, n_tokens, prm, st);
+  if (want_ew8) return launch_tc<2, 256, 2, false, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 1) return launch_tc<1, 256, 3, false>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 2) return launch_tc<2, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
   return launch_tc<3, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
