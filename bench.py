@@ -254,11 +254,11 @@ def main():
     search = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode="nccl")
 
     def step():
-        Qb, qm32 = evdr.pack_queries(Q, qm)                          # 1 launch
-        pk.score_packed(Qb, qm32, out=scores)                        # 1 launch (maxsim_tc_kernel)
-        return search.topk(scores, TOPK)                             # 2 launches (+2 and the all-gather for N>1)
-
-    launches_per_step = 4 if n_gpus == 1 else 6
+        Qb, qm32 = evdr.pack_queries(Q, qm)                          # 1 launch  (pack_queries_kernel)
+        pk.score_packed(Qb, qm32, out=scores)                        # 1 launch  (maxsim_tc_kernel)
+        return search.topk(scores, TOPK)                             # 1 launch  (topk_select_kernel); N > 1:
+                                                                     # + unpack_gathered + merge (+ NCCL's own)
+    launches_per_step = 3 if n_gpus == 1 else 5
 
     def barrier():
         if world > 1:
