@@ -18,23 +18,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// remote arrive on the same-offset barrier of CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(cta) : "memory");
 }
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or
 // the hint (ns) expires, instead of re-polling every ~50 ns and stealing issue slots from the
@@ -191,23 +180,8 @@ __device__ __forceinline__ void mma_commit_cg2_mc(uint32_t bar, uint16_t cta_mas
       ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
-// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns, and wait.
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t taddr, float (&v)[32]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-// issue only (no wait); pair with tmem_wait_ld_tied on the same registers
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns; issue only (no wait),
+// pair with tmem_wait_ld_tied on the same registers
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -243,17 +217,6 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return d;
 }
 
-// max(rm, v[0..31]) as a depth-4 tree of 3-input maxes: 16 FMNMX3 with one op on the rm chain
-__device__ __forceinline__ float max_tree32(float rm, const float (&v)[32]) {
-  float a[10];
-#pragma unroll
-  for (int j = 0; j < 10; ++j) a[j] = max3(v[3 * j], v[3 * j + 1], v[3 * j + 2]);
-  const float b0 = max3(a[0], a[1], a[2]);
-  const float b1 = max3(a[3], a[4], a[5]);
-  const float b2 = max3(a[6], a[7], a[8]);
-  const float b3 = max3(a[9], v[30], v[31]);
-  return max3(rm, max3(b0, b1, b2), b3);
-}
 // max(v[o..o+15]): 7 FMNMX3 + 1 FMNMX, depth 3
 __device__ __forceinline__ float max16(const float (&v)[32], int o) {
   const float a0 = max3(v[o + 0], v[o + 1], v[o + 2]);
@@ -279,18 +242,6 @@ __device__ __forceinline__ int first_pos16(const float (&v)[32], int o, float m)
   for (int i = 14; i >= 0; --i) pos = (v[o + i] == m) ? i : pos;
   return pos;
 }
-// max(rm, v[o..o+15]): 8 FMNMX3, depth 3
-__device__ __forceinline__ float max_tree16(float rm, const float (&v)[32], int o) {
-  const float a0 = max3(v[o + 0], v[o + 1], v[o + 2]);
-  const float a1 = max3(v[o + 3], v[o + 4], v[o + 5]);
-  const float a2 = max3(v[o + 6], v[o + 7], v[o + 8]);
-  const float a3 = max3(v[o + 9], v[o + 10], v[o + 11]);
-  const float a4 = max3(v[o + 12], v[o + 13], v[o + 14]);
-  const float b0 = max3(a0, a1, a2);
-  const float b1 = max3(a3, a4, v[o + 15]);
-  return max3(rm, b0, b1);
-}
-
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile in the canonical SWIZZLE_128B layout: rows of 128 B (64 bf16), 8-row
 // swizzle atoms of 1024 B laid back to back (SBO = 1024 B), tile base 1024-B aligned.

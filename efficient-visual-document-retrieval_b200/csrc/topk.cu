@@ -15,12 +15,6 @@ namespace evdr {
 constexpr int TOPK_MAX = 128;
 constexpr int TOPK_WARPS = 8;
 
-struct Cand {
-  float s;
-  int tie;
-  long long id;
-};
-
 __device__ __forceinline__ bool better(float s, long long t, float os, long long ot) {
   return (s > os) || (s == os && t < ot);
 }
