@@ -55,7 +55,7 @@ struct TcParams {
 // KB = number of 128-wide K blocks of the operands: 1 = plain bf16; 3 = the bf16x3 split
 // A = [Qhi | Qhi | Qlo], B = [Phi | Plo | Phi] whose K = 384 contraction is Qhi.Phi + Qhi.Plo + Qlo.Phi,
 // i.e. the fp32 dot product up to the dropped Qlo.Plo term (~2^-18 relative) -- the high-fidelity mode
-template <int R, int BN, int STAGES, bool CG2, int KB = 1>
+template <int R, int BN, int STAGES, bool CG2, int KB = 1, bool SP = false, int EW = 4>
 struct TcCfg {
   static constexpr int B_ROWS = CG2 ? BN / 2 : BN;          // page tokens held by this CTA per stage
   static constexpr int KSUB = 2 * KB;                        // 64-wide K sub-tiles per operand tile
@@ -69,7 +69,12 @@ struct TcCfg {
   // then the scheduler ring: slot_full[NSLOT], slot_empty[NSLOT], item[NSLOT]
   static constexpr int NSLOT = 4;
   static constexpr int BAR_BYTES = 8 * (2 * STAGES + 6) + 8 + 8 * 2 * NSLOT + 4 * NSLOT;
-  static constexpr int TOTAL = BAR_OFF + BAR_BYTES + 1024;  // + alignment slack
+  // short-page variant: per epilogue warp a [16 pages][32 tokens (+1 pad)] fp32 staging area where the
+  // per-token maxes of the pages completed in a tile wait for their 32-token sums
+  static constexpr int STG_ROW = 33;
+  static constexpr int STG_BYTES = SP ? EW * (BN / EVDR_CHUNK) * STG_ROW * 4 : 0;
+  static constexpr int STG_OFF = BAR_OFF + ((BAR_BYTES + 15) / 16) * 16;
+  static constexpr int TOTAL = STG_OFF + STG_BYTES + 1024;  // + alignment slack
   static constexpr int TILES_PER_GROUP = CG2 ? 2 * R : R;
 };
 
@@ -83,7 +88,7 @@ template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                  const TcParams prm) {
-  using S = TcCfg<R, BN, STAGES, CG2, KB>;
+  using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW>;
   constexpr int A_TILE_BYTES = S::A_TILE_BYTES;
   constexpr int KSUB = S::KSUB;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
@@ -279,6 +284,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     // ===================================================== epilogue warps
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
     const int egrp = (warp - 2) >> 2;                    // EW == 8: epilogue group 0 / 1 <-> query tile r
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + S::STG_OFF) +
+                 (warp - 2) * (BN / EVDR_CHUNK) * S::STG_ROW;   // SP: this warp's staging rows
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t acc_it = 0;
     int cur_g = -1;
@@ -407,14 +414,6 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                   prm.argmax[(size_t)p * ((size_t)prm.nq * prm.lq) + (size_t)qidx[r] * prm.lq + lane] = slot;
                 pstart = pe;
                 bc = pe;
-              } else if constexpr (SP) {
-                const float v = rm * qm[r];
-                if (nfin == 0) fin_page0 = p;
-                f0 = nfin == 0 ? v : f0;
-                f1 = nfin == 1 ? v : f1;
-                f2 = nfin == 2 ? v : f2;
-                f3 = nfin == 3 ? v : f3;
-                if (++nfin == 4) flush();
               } else {
                 const float s = warp_sum(rm * qm[r]);
                 if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
@@ -457,16 +456,50 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               }
             }
             // ---- fold the chunk maxes into the running per-page max; a page can end after any chunk
+            if constexpr (SP && !AM) {
+              // short pages: which of this tile's chunks close a page, as a bit mask built with one
+              // redux.or over the lane-cached page ends of the current and the next batch of 32 pages
+              // (pages already finished end at or before the tile start, pages past the item's end are
+              // INT_MAX: neither sets a bit); then ONE pass over the 16 chunk maxes.
+              auto end_bit = [&](int pev) {
+                const int pos = pev - ch_tile0 - 1;
+                return (pos >= 0 && pos < CH_PER_TILE) ? (1u << pos) : 0u;
+              };
+              const unsigned endmask = __reduce_or_sync(0xffffffffu, end_bit(pe_cache) | end_bit(pe_next));
+              const float w = qm[r];
+              int k = 0;                               // pages completed in this tile so far
+#pragma unroll
+              for (int j = 0; j < CH_PER_TILE; ++j) {
+                rm = fmaxf(rm, h[j]);
+                if (endmask & (1u << j)) {             // warp-uniform: chunk j closes page p + k
+                  stg[k * S::STG_ROW + lane] = rm * w;  // per-token max of the finished page
+                  ++k;
+                  rm = -INFINITY;
+                }
+              }
+              if (k > 0) {
+                // 32-token sums of the k finished pages: lane l adds up row l (conflict-free thanks to
+                // the 33-float row pitch), then k lanes store k consecutive scores at once
+                __syncwarp();
+                if (lane < k) {
+                  float sacc = 0.f;
+#pragma unroll
+                  for (int t = 0; t < 32; ++t) sacc += stg[lane * S::STG_ROW + t];
+                  if (qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p + lane] = sacc;
+                }
+                __syncwarp();
+                p += k;
+              }
+              const int b = (p - p0) >> 5;
+              if (b != cb) set_batch(b);
+              pe = __shfl_sync(0xffffffffu, pe_cache, (p - p0) & 31);
+            } else {
             const bool whole_tile = !AM && (pe >= ch_tile0 + CH_PER_TILE);
             if (whole_tile) {
-              if constexpr (SP && CH_PER_TILE == 16) {
-                rm = max_tree16r(rm, h);
-              } else {
-                float m = rm;
+              float m = rm;
 #pragma unroll
-                for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, h[j], h[j + 1]);
-                rm = m;
-              }
+              for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, h[j], h[j + 1]);
+              rm = m;
               if (pe == ch_tile0 + CH_PER_TILE) finalize();
             } else {
               // compact (not unrolled) segment loop: ONE copy of finalize per resident tile keeps the
@@ -485,29 +518,16 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                     bc = take ? ch_tile0 + j : bc;
                     bp = take ? hp[j] : bp;
                   }
-                } else if constexpr (!SP) {
+                } else {
 #pragma unroll
                   for (int j = 0; j < CH_PER_TILE; ++j)
                     rm = (j >= lo && j < hi) ? fmaxf(rm, h[j]) : rm;
-                } else {
-                  // masked tree: one op on the rm chain per segment instead of one per chunk
-                  float g[CH_PER_TILE];
-#pragma unroll
-                  for (int j = 0; j < CH_PER_TILE; ++j) g[j] = (j >= lo && j < hi) ? h[j] : -INFINITY;
-                  if constexpr (CH_PER_TILE == 16) {
-                    rm = max_tree16r(rm, g);
-                  } else {
-                    float m = rm;
-#pragma unroll
-                    for (int j = 0; j + 1 < CH_PER_TILE; j += 2) m = max3(m, g[j], g[j + 1]);
-                    rm = m;
-                  }
                 }
                 if (pe - ch_tile0 <= CH_PER_TILE) finalize();
                 lo = hi;
               }
             }
-            if constexpr (!AM && SP) { if (nfin > 0) flush(); }
+            }
             runmax[r] = rm;
             best_chunk[r] = bc;
             best_pos[r] = bp;
@@ -547,7 +567,7 @@ static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uin
 template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4>
 static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens,
                      TcParams prm, cudaStream_t st) {
-  using S = TcCfg<R, BN, STAGES, CG2, KB>;
+  using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW>;
   CUtensorMap tmQ, tmP;
   int rc = encode_2d_bf16(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, 128, KB, "queries");
   if (rc != EVDR_OK) return rc;
@@ -630,9 +650,17 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   if (k_blocks == 3) { R = 1; tpg = 1; }   // bf16x3: one resident query tile (96 KB), 64-token page tiles
   // pages shorter than half a tile end several times per tile: the epilogue (not the MMA) is the
   // limit there -> two epilogue groups, one per resident query tile
-  const bool short_pages = !pair && !argmax && k_blocks == 1 && prm.nqt >= 2 &&
-                           (double)total_chunks / (double)np < 8.0;
-  const bool want_ew8 = mode && strcmp(mode, "ew8") == 0 && !pair && !argmax && k_blocks == 1 && prm.nqt >= 2;
+  // Two epilogue groups (8 warps, R = 2) measured best whenever there are enough query tiles to
+  // balance groups of two: pages shorter than two tiles use the end-mask + staged-sum epilogue (SP,
+  // 1480-1494 TFLOP/s from 16- to 208-token pages vs 775-1195 with one group), longer pages the tree
+  // fold (1500 vs 1478 TFLOP/s at 1024 queries).  EVDR_TC_MODE=1cta keeps one group with R <= 3.
+  const bool one_group = mode && strcmp(mode, "1cta") == 0;
+  const bool two_groups_ok = !pair && !argmax && k_blocks == 1 && !one_group;
+  const double avg_chunks = (double)total_chunks / (double)np;
+  const bool force_sp8 = mode && strcmp(mode, "sp8") == 0;
+  const bool short_pages = two_groups_ok && prm.nqt >= 2 && (avg_chunks < 32.0 || force_sp8);
+  const bool want_ew8 = two_groups_ok && !short_pages &&
+                        (prm.nqt >= 16 || (mode && strcmp(mode, "ew8") == 0 && prm.nqt >= 2));
   if (short_pages || want_ew8) { R = 2; tpg = 2; }
   const int n_qgroups = (prm.nqt + tpg - 1) / tpg;
   const int units = pair ? h->sm_count / 2 : h->sm_count;

@@ -39,16 +39,17 @@ def test_medium_case(evdr, cuda):
     U.assert_scores_close(out.cpu().numpy(), z["out"])
 
 
-@pytest.mark.parametrize("mode", ["pair", "1cta"])
+@pytest.mark.parametrize("mode", ["pair", "1cta", "default", "sp8", "ew8"])
 @pytest.mark.parametrize("nq", [1, 3, 4, 5, 8, 9, 12, 13, 16, 17, 24, 25, 32, 33, 40, 100])
 def test_query_tile_configs_vs_exact_kernel(evdr, cuda, nq, mode, monkeypatch):
-    """Every kernel flavour: single-CTA (cta_group::1) with R = 1, 2, 3 resident query tiles and CTA
-    pairs (cta_group::2) with R = 1..4 per CTA, incl. partial last tiles, odd tile counts (the peer
-    CTA's tile is out of range) and partial last groups."""
-    if mode == "pair":
-        monkeypatch.setenv("EVDR_TC_MODE", "pair")
-    else:
+    """Every kernel flavour: one epilogue group with R = 1, 2, 3 resident query tiles ("1cta"), two
+    epilogue groups with the tree fold ("ew8") or the end-mask / staged-sum epilogue ("sp8"), CTA pairs
+    (cta_group::2) with R = 1..4 per CTA, and the default dispatch -- incl. partial last tiles, odd tile
+    counts and partial last groups."""
+    if mode == "default":
         monkeypatch.delenv("EVDR_TC_MODE", raising=False)
+    else:
+        monkeypatch.setenv("EVDR_TC_MODE", mode)
     P, pm = evdr.synth.make_pages(150, 1030, seed=100 + nq, device=cuda, n_holes=6, empty_frac=0.02)
     Q, qm, rel = evdr.synth.make_queries(P, pm, nq, 32, seed=200 + nq, sigma=3.0, min_len=8, drop=0.1)
     evdr.retrieval.clear_pack_cache()
