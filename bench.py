@@ -148,11 +148,17 @@ def cpu_reference_rate(seconds_target: float = 12.0, n_queries: int = 32):
     rate = n_queries * 64 / (time.perf_counter() - t0)
     n_pages = int(max(64, min(4096, (rate * seconds_target / n_queries) // 64 * 64)))
     Q, P, qm, pm = sample(n_pages)
-    t0 = time.perf_counter()
-    maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
-    dt = time.perf_counter() - t0
-    return {"value": n_queries * n_pages / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n_queries} queries x {n_pages} pages x {LP_VALID} tokens fp32, chunk_p=64, {dt:.2f} s"}, (Q, P, qm, pm)
+    # at least `seconds_target` of CPU work: the page sample is capped at 4096 pages (2.2 GB fp32), faster
+    # hosts repeat the same pass
+    reps, dt = 0, 0.0
+    while reps == 0 or (dt < seconds_target and reps < 64):
+        t0 = time.perf_counter()
+        maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
+        dt += time.perf_counter() - t0
+        reps += 1
+    return {"value": reps * n_queries * n_pages / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{reps} pass(es) of {n_queries} queries x {n_pages} pages x {LP_VALID} tokens fp32, chunk_p=64, "
+                      f"{dt:.2f} s in total"}, (Q, P, qm, pm)
 
 
 def run_reference_arm(args):
@@ -311,11 +317,15 @@ def main():
     ms_kernel = timed(lambda: pk.score_packed(Qb, qm32, out=scores), args.steps, 1)
     flops = nq * npg * FLOPS_PER_PAIR
     achieved = flops / (ms_kernel * 1e-3) / 1e12
+    # denominator: the measured BURST cuBLAS bf16 peak (the higher of the two measured figures, so the
+    # fraction can only be understated); each launch runs ~0.57 s at the power cap, where cuBLAS itself
+    # sustains bf16_tflops_sustained -- reported beside it
     roofline = {"kernel": "maxsim_tc_kernel", "bound": "tensor", "achieved": achieved,
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"],
-                "peak_kind": f"{peaks['source']} sustained cuBLAS bf16 (each launch runs {ms_kernel:.0f} ms, power-capped regime)",
-                "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "burst_peak": peaks["bf16_tflops"],
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"],
+                "peak_kind": f"{peaks['source']} burst cuBLAS bf16 (8192^3, best of 10)",
+                "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
+                "sustained_peak": peaks["bf16_tflops_sustained"],
                 "ms_per_launch": ms_kernel, "algorithmic_flops_per_launch": flops,
                 "algorithmic_bytes_per_launch": npg * BYTES_PER_PAGE, "traffic": measured_traffic(nq, npg)}
 

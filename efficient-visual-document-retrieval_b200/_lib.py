@@ -54,6 +54,9 @@ _SIGNATURES = {
     "evdr_sharded_topk": ([_vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp], _i),
     "evdr_l2norm_fwd": ([_vp, _vp, _vp, _i64, _i, _vp, _vp], _i),
     "evdr_l2norm_bwd": ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp], _i),
+    "evdr_rank_gap": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "evdr_liscore_loss": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _i, C.c_float, _vp, _vp, _vp, _vp, _vp], _i),
+    "evdr_pairwise_loss": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

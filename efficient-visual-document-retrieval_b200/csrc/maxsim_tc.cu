@@ -672,11 +672,18 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     const double avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
     ppi = (int)(65536.0 / avg_tok + 0.5);
     if (ppi < 1) ppi = 1;
-    // ... but the `units` items in flight span units / n_qgroups page blocks, which must stay
-    // L2-resident (126 MB) for the other query groups' re-reads to hit: cap the window at ~48 MB
-    if (n_qgroups > 1) {
+    // ... with few query groups every page block is re-read by only a handful of CTAs while the grid
+    // spans units / n_qgroups blocks: keep that window L2-resident (~48 MB of the 126 MB) ...
+    if (n_qgroups > 1 && n_qgroups < 8) {
       const double cap = 48e6 * n_qgroups / ((double)units * avg_tok * EVDR_TC_DIM * 2 * k_blocks);
       if (ppi > cap) ppi = cap < 8.0 ? 8 : (int)cap;   // >= 8 pages: keep the query-tile reload amortised
+    } else if (n_qgroups >= 8 && n_qgroups < 64) {
+      // ... from 8 groups on the CTAs of a block run in step (dynamic scheduler) and the window is not
+      // the limit: measured DRAM traffic stays 1.03x algorithmic up to 64K-token items at 64 and 256
+      // queries, and 32K-token items amortise the query-tile reload at every item change best
+      // (64 queries: 1444 -> 1494 TFLOP/s; profiles/r1g_item_size_sweep.log)
+      const int p32k = (int)(32768.0 / avg_tok + 0.5);
+      if (ppi > p32k) ppi = p32k < 1 ? 1 : p32k;
     }
     if (ppi >= 16) ppi = (ppi / 16) * 16;
     // ... and there must be enough items to balance the grid

@@ -132,12 +132,19 @@ class _MaxSimRescoreFn(torch.autograd.Function):
         lib = _lib.load()
         h = _lib.handle(dev)
         st = _lib.stream_ptr(dev)
-        # bf16x3 split operands: the search runs at ~fp32 accuracy, so the winners are the reference's
-        Qb, qm32 = pack_queries(Q, qm, 3)
+        # bf16x3 split operands: the search runs at ~fp32 accuracy, so the winners are the reference's.
+        # Queries of 33..128 tokens arrive zero-padded to a multiple of 32 (score_multi_vector_masked) and
+        # are searched as nq*G rows of 32 tokens: row-major (nq, G*32) IS (nq*G, 32), so the argmax table
+        # [np, nq*lq] needs no re-indexing
+        G = 1
+        if lq > TC_LQ:
+            assert lq % TC_LQ == 0, "long queries must be padded to a multiple of 32 tokens"
+            G = lq // TC_LQ
+        Qb, qm32 = pack_queries(Q.view(nq * G, lq // G, d), qm.view(nq * G, lq // G), 3)
         pk = PackedPages.from_padded(P, pm, normalize=False, varlen=False, k_blocks=3)
         R = nq * lq
         am = torch.empty((npg, R), dtype=torch.int32, device=dev)
-        _lib.check(lib.evdr_maxsim_packed_argmax(h, Qb.data_ptr(), qm32.data_ptr(), nq, lq, pk.tokens.data_ptr(),
+        _lib.check(lib.evdr_maxsim_packed_argmax(h, Qb.data_ptr(), qm32.data_ptr(), nq * G, lq // G, pk.tokens.data_ptr(),
                                                  pk.tokens.shape[0], pk.chunk_off.data_ptr(), npg,
                                                  pk.total_chunks, 3, am.data_ptr(), st), "evdr_maxsim_packed_argmax")
         out = torch.empty((nq, npg), dtype=torch.float32, device=dev)
@@ -245,7 +252,7 @@ def score_multi_vector_masked(
         return torch.zeros((nq, npg), dtype=torch.float32, device=Q.device)
     precision = precision or os.environ.get("EVDR_PRECISION", "bf16")
     needs_grad = torch.is_grad_enabled() and (Q.requires_grad or P.requires_grad)
-    if precision == "fp32" or d != TC_DIM or lq > TC_LQ_MAX or (needs_grad and lq > TC_LQ):
+    if precision == "fp32" or d != TC_DIM or lq > TC_LQ_MAX:
         return maxsim_exact(Q, P, qmask, pmask)
     if precision == "bf16x3" and not needs_grad:
         # high-fidelity tensor-core mode for operands that are not bf16-representable
@@ -253,7 +260,14 @@ def score_multi_vector_masked(
             return PackedPages.from_padded(P.detach(), pmask, k_blocks=3).score(Q.detach(), qmask)
     if needs_grad:
         # training: tensor-core search + fp32 rescoring of the winners, backward through the same indices
-        return _MaxSimRescoreFn.apply(_float_operand(Q), _float_operand(P), _mask_u8(qmask), _mask_u8(pmask))
+        Qf, qm8 = _float_operand(Q), _mask_u8(qmask)
+        if lq > TC_LQ and lq % TC_LQ:
+            # 33..128-token queries: masked zero tokens up to a multiple of 32 (they add 0 to every score
+            # and receive no gradient; autograd slices dQ back)
+            pad = TC_LQ - lq % TC_LQ
+            Qf = torch.nn.functional.pad(Qf, (0, 0, 0, pad))
+            qm8 = torch.nn.functional.pad(qm8, (0, pad))
+        return _MaxSimRescoreFn.apply(Qf, _float_operand(P), qm8, _mask_u8(pmask))
     with torch.no_grad():
         return _packed_for(P.detach(), pmask).score(Q.detach(), qmask)   # lq > 32: scored as 32-token groups
 

@@ -260,6 +260,39 @@ EVDR_API int evdr_l2norm_bwd(evdr_handle* h, const float* X_dev, const uint8_t* 
                              const float* gY_dev, int64_t n_tok, int d, float* gX_dev,
                              void* stream);
 
+/* ------------------------------------------------------------------------
+ * The (B, N) score-matrix consumers directly behind the scorer in a training step.
+ * Scores are fp32 [B, ld] rows (first n columns used).  Everything is deterministic.
+ *
+ * evdr_rank_gap -- mainv3_iter_liscore_QA_hardtoken.py:368-385 in one launch:
+ *   rank_x[b,i] = position of page i in the descending order of row b (the reference's
+ *                 argsort(argsort(x, descending=True)); equal scores keep index order),
+ *   gap = rank_t - rank_s (fp32, :371), G[i] = sum_b |gap[b,i]| (:372),
+ *   topk_idx[b, 0..kk) = the teacher's kk best pages, best first (:377-378),
+ *   aux_idx[b, 0..a)   = those of them with the largest |gap|, largest first (:379-382; equal gaps
+ *                        keep teacher-rank order).
+ *   Any output pointer may be NULL.  0 <= a <= kk <= min(n, 1024), B*n < 2^24.
+ * evdr_liscore_loss -- criterion.py:123-142 (listwise_distillation_loss: top-k partial cross entropy
+ *   between temperature softmaxes, times T^2) and criterion.py:81-83 (score_preserving_loss = MSE),
+ *   forward AND d/d(sc_s) of each, one launch:  loss2[0] = listwise, loss2[1] = mse,
+ *   grad_listwise / grad_mse fp32 [B, n].  row_loss_ws: scratch of 2*B floats.  k > n is an error like
+ *   torch.topk's.
+ * evdr_pairwise_loss -- criterion.py:96-110 (pairwise_distillation_loss = mean BCE-with-logits of all
+ *   score differences against sigmoid(teacher differences)) and its gradient without the three
+ *   (B, N, N) intermediates.  part_ws: scratch of B * ceil(n / 256) floats.
+ * ------------------------------------------------------------------------ */
+EVDR_API int evdr_rank_gap(evdr_handle* h, const float* sc_t_dev, int64_t ld_t, const float* sc_s_dev,
+                           int64_t ld_s, int B, int n, int kk, int a, float* gap_dev, float* G_dev,
+                           int32_t* rank_t_dev, int32_t* rank_s_dev, int64_t* topk_idx_dev,
+                           int64_t* aux_idx_dev, void* stream);
+EVDR_API int evdr_liscore_loss(evdr_handle* h, const float* sc_s_dev, int64_t ld_s, const float* sc_t_dev,
+                               int64_t ld_t, int B, int n, int k, float temperature,
+                               float* grad_listwise_dev, float* grad_mse_dev, float* row_loss_ws_dev,
+                               float* loss2_dev, void* stream);
+EVDR_API int evdr_pairwise_loss(evdr_handle* h, const float* sc_s_dev, int64_t ld_s, const float* sc_t_dev,
+                                int64_t ld_t, int B, int n, float* grad_dev, float* part_ws_dev,
+                                float* loss1_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,6 +161,43 @@ def test_rescore_path_vs_exact_on_fp32_operands(evdr, cuda):
         assert rel < 1e-2 and frac > 0.995, (rel, frac)
 
 
+@pytest.mark.parametrize("lq", [33, 50, 64, 100])
+def test_long_query_gradient_calls_use_tensor_cores(evdr, cuda, lq, monkeypatch):
+    """ColPali queries run to 50 tokens (process_queries max_length, evaluator/retrieval.py:63): gradient
+    calls with 33..128 query tokens are padded to 32-token groups for the tensor-core search and must equal
+    the exact fp32 path in scores and in dP / dQ (which keep the caller's (nq, lq, d) shape)."""
+    g = torch.Generator(device=cuda).manual_seed(lq)
+    npg, ls, nq = 120, 70, 9
+    P = torch.randn(npg, ls, 128, generator=g, device=cuda)
+    pm = torch.rand(npg, ls, generator=g, device=cuda) > 0.2
+    pm[3] = False
+    P = evdr.l2_normalize_masked(P, pm)
+    Q = torch.nn.functional.normalize(torch.randn(nq, lq, 128, generator=g, device=cuda), dim=-1)
+    qm = torch.rand(nq, lq, generator=g, device=cuda) > 0.15
+    gout = torch.randn(nq, npg, generator=g, device=cuda)
+    import evdr_b200.retrieval as R
+    calls = []
+    orig = R._MaxSimRescoreFn.forward
+    monkeypatch.setattr(R._MaxSimRescoreFn, "forward", staticmethod(lambda ctx, *a: (calls.append(1), orig(ctx, *a))[1]))
+    outs, grads = [], []
+    for prec in (None, "fp32"):
+        Pg = P.clone().requires_grad_(True)
+        Qg = Q.clone().requires_grad_(True)
+        o = evdr.score_multi_vector_masked(Qg, Pg, qm, pm, 64, precision=prec)
+        o.backward(gout)
+        outs.append(o.detach())
+        grads.append((Pg.grad, Qg.grad))
+    assert len(calls) == 1, "the default precision must take the tensor-core search + rescore path"
+    assert grads[0][1].shape == (nq, lq, 128)
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=2e-5, atol=2e-5)
+    assert (outs[0][:, 3] == 0).all()
+    assert grads[0][1][~qm].abs().max() == 0, "masked query tokens receive exactly zero gradient"
+    for a, b in zip(grads[0], grads[1]):
+        rel = ((a - b).norm() / b.norm()).item()
+        frac = torch.isclose(a, b, rtol=1e-4, atol=1e-6).float().mean().item()
+        assert rel < 1e-2 and frac > 0.995, (rel, frac)
+
+
 @pytest.mark.parametrize("nq,npg,lp", [(13, 200, 1030), (40, 500, 64), (5, 60, 333)])
 def test_bf16x3_high_fidelity_mode(evdr, cuda, nq, npg, lp):
     """precision='bf16x3': K = 384 split operands on the tensor cores reproduce the fp32 scores of

@@ -1,0 +1,148 @@
+"""GPU parity of the score-matrix consumers (losses.cu) against the golden outputs of the unmodified
+reference (tests/golden/losses.npz: criterion.py losses + autograd, rank-gap block of
+mainv3_iter_liscore_QA_hardtoken.py:368-385) and against the float64 oracle on other shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle as lo
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["b32_n500_k10", "b32_n1000_k40_T05", "b5_n70_k40_T2", "b1_n12_k12"]
+# fp32 kernels vs the reference's fp32 torch ops: summation order only
+LOSS_RTOL, GRAD_RTOL = 2e-5, 2e-4
+
+
+def _case(name, cuda):
+    z = np.load(U.GOLDEN / "losses.npz")
+    B, N, k, aux, _ = (int(v) for v in z[f"{name}/spec"])
+    s = torch.from_numpy(z[f"{name}/s"]).to(cuda)
+    t = torch.from_numpy(z[f"{name}/t"]).to(cuda)
+    return z, B, N, k, aux, float(z[f"{name}/T"]), s, t
+
+
+def _close_grad(got, ref, what):
+    np.testing.assert_allclose(got, ref, rtol=GRAD_RTOL, atol=2e-6 * np.abs(ref).max(), err_msg=what)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_losses_match_reference(evdr, cuda, name):
+    z, B, N, k, aux, T, s, t = _case(name, cuda)
+    for key, fn in (("listwise", lambda x: evdr.listwise_distillation_loss(x, t, k=k, temperature=T)),
+                    ("mse", lambda x: evdr.score_preserving_loss(x, t)),
+                    ("pairwise", lambda x: evdr.pairwise_distillation_loss(x, t))):
+        sg = s.clone().requires_grad_(True)
+        loss = fn(sg)
+        assert loss.shape == () and loss.dtype == torch.float32 and loss.device == s.device
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), z[f"{name}/{key}_loss"], rtol=LOSS_RTOL, err_msg=key)
+        _close_grad(sg.grad.cpu().numpy(), z[f"{name}/{key}_grad"], key)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_liscore_combination_is_one_launch_and_linear(evdr, cuda, name):
+    """The *_liscore recipes add lambda_list * listwise + lambda_score * mse (mainv2_iter_liscore.py:
+    301-303): both come from one evdr_liscore_loss call and the backward combines the two gradients."""
+    z, B, N, k, aux, T, s, t = _case(name, cuda)
+    sg = s.clone().requires_grad_(True)
+    ll, lm = evdr.liscore_losses(sg, t, k=k, temperature=T)
+    (0.7 * ll + 0.25 * lm).backward()
+    want = 0.7 * z[f"{name}/listwise_grad"] + 0.25 * z[f"{name}/mse_grad"]
+    _close_grad(sg.grad.cpu().numpy(), want, "combined")
+    # bit-reproducible
+    sg2 = s.clone().requires_grad_(True)
+    ll2, lm2 = evdr.liscore_losses(sg2, t, k=k, temperature=T)
+    (0.7 * ll2 + 0.25 * lm2).backward()
+    assert torch.equal(ll, ll2) and torch.equal(lm, lm2) and torch.equal(sg.grad, sg2.grad)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_rank_gap_matches_reference(evdr, cuda, name):
+    z, B, N, k, aux, T, s, t = _case(name, cuda)
+    rg = evdr.rank_gap(t, s, k=k, aux_docs=aux)
+    for got, key in ((rg.rank_t, "rank_t"), (rg.rank_s, "rank_s"), (rg.gap, "gap"), (rg.G, "G"),
+                     (rg.topk_idx, "topk_idx")):
+        np.testing.assert_array_equal(got.cpu().numpy(), z[f"{name}/{key}"], err_msg=key)   # bit-exact
+    gap = np.abs(z[f"{name}/gap"])
+    rows = np.arange(B)[:, None]
+    got_aux = rg.aux_doc_idx.cpu().numpy()
+    assert got_aux.shape == z[f"{name}/aux_doc_idx_q"].shape
+    # same |gap| values in the same order; equal gaps may name another page of the teacher's top-k
+    np.testing.assert_array_equal(gap[rows, got_aux], gap[rows, z[f"{name}/aux_doc_idx_q"]])
+    assert all(set(got_aux[b]) <= set(z[f"{name}/topk_idx"][b]) for b in range(B))
+
+
+@pytest.mark.parametrize("B,N,k,T", [(1, 1, 1, 1.0), (3, 257, 100, 0.07), (64, 2048, 10, 1.0), (1663, 277, 10, 1.0),
+                                     (300, 277, 40, 0.5)])
+def test_losses_vs_oracle_other_shapes(evdr, cuda, B, N, k, T):
+    g = torch.Generator().manual_seed(B + N)
+    t = 12.0 + 3.0 * torch.randn(B, N, generator=g)
+    s = t + 1.5 * torch.randn(B, N, generator=g)
+    sd, td = s.to(cuda), t.to(cuda)
+    pairs = [("listwise", lambda x: evdr.listwise_distillation_loss(x, td, k=k, temperature=T),
+              lo.listwise_distillation_loss(s.numpy(), t.numpy(), k, T)),
+             ("mse", lambda x: evdr.score_preserving_loss(x, td), lo.score_preserving_loss(s.numpy(), t.numpy()))]
+    if B * N * N <= 60_000_000:
+        pairs.append(("pairwise", lambda x: evdr.pairwise_distillation_loss(x, td),
+                      lo.pairwise_distillation_loss(s.numpy(), t.numpy())))
+    for key, fn, (ref_loss, ref_grad) in pairs:
+        sg = sd.clone().requires_grad_(True)
+        loss = fn(sg)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), ref_loss, rtol=5e-5, atol=1e-7, err_msg=key)
+        np.testing.assert_allclose(sg.grad.cpu().numpy(), ref_grad, rtol=1e-3,
+                                   atol=5e-6 * max(np.abs(ref_grad).max(), 1e-30), err_msg=key)
+
+
+def test_rank_gap_ties_keep_index_order_and_strided_rows(evdr, cuda):
+    t = torch.tensor([[1.0, 3.0, 3.0, 0.5, 3.0], [2.0, 2.0, 2.0, 2.0, 2.0]], device=cuda)
+    s = torch.tensor([[5.0, 4.0, 3.0, 2.0, 1.0], [1.0, 2.0, 3.0, 4.0, 5.0]], device=cuda)
+    wide = torch.zeros(2, 9, device=cuda)
+    wide[:, :5] = t
+    rg = evdr.rank_gap(wide[:, :5], s, k=3, aux_docs=2)          # non-contiguous rows (ld = 9)
+    ref = lo.rank_gap(t.cpu().numpy(), s.cpu().numpy(), 3, 2)
+    assert rg.rank_t.tolist() == [[3, 0, 1, 4, 2], [0, 1, 2, 3, 4]]
+    for key in ("rank_t", "rank_s", "gap", "G", "topk_idx", "aux_doc_idx"):
+        np.testing.assert_array_equal(getattr(rg, key).cpu().numpy(), ref[key], err_msg=key)
+
+
+def test_loss_argument_errors(evdr, cuda):
+    s = torch.zeros(2, 5, device=cuda)
+    with pytest.raises(ValueError):                       # torch.topk raises when k > N (criterion.py:132)
+        evdr.listwise_distillation_loss(s, s, k=6)
+    with pytest.raises(ValueError):
+        evdr.pairwise_distillation_loss(s, torch.zeros(2, 6, device=cuda))
+    with pytest.raises(evdr._lib.EvdrError):              # no CPU fallback
+        evdr.score_preserving_loss(s.cpu(), s.cpu())
+
+
+def test_training_step_with_fused_losses(evdr, cuda):
+    """Scorer -> fused liscore loss -> scorer backward: gradient on the student pages equals the one
+    obtained with the same losses written in torch (the reference's criterion.py formulas)."""
+    import torch.nn.functional as F
+    g = torch.Generator(device=cuda).manual_seed(11)
+    npg, ls, nq = 200, 41, 32
+    Pt, pmt = evdr.synth.make_pages(npg, 206, seed=5, device=cuda, n_holes=3, empty_frac=0.0, min_len=60)
+    Q, qm, _ = evdr.synth.make_queries(Pt, pmt, nq, 32, seed=6, sigma=1.0, min_len=8, drop=0.1)
+    Pbar = torch.randn(npg, ls, 128, generator=g, device=cuda)
+    pms = torch.rand(npg, ls, generator=g, device=cuda) > 0.1
+    with torch.no_grad():
+        sc_t = evdr.score_multi_vector_masked(Q, Pt, qm, pmt, 32)
+    grads = []
+    for fused in (True, False):
+        param = Pbar.clone().requires_grad_(True)
+        Ps = evdr.l2_normalize_masked(param, pms)
+        sc_s = evdr.score_multi_vector_masked(Q, Ps, qm, pms, 32)
+        if fused:
+            ll, lm = evdr.liscore_losses(sc_s, sc_t, k=10, temperature=1.0)
+        else:
+            lps, pt = F.log_softmax(sc_s, dim=1), F.softmax(sc_t, dim=1)
+            _, idx = torch.topk(pt, 10, dim=1)
+            ll = -(pt.gather(1, idx) * lps.gather(1, idx)).sum(1).mean()
+            lm = F.mse_loss(sc_s, sc_t)
+        (1.0 * ll + 0.5 * lm).backward()
+        grads.append(param.grad)
+    rel = ((grads[0] - grads[1]).norm() / grads[1].norm()).item()
+    assert rel < 1e-4, rel

@@ -145,3 +145,39 @@ def test_ndcg_cross_check_with_sklearn():
             mine = to.per_query_measures(qrel, ranking, [k])[f"ndcg@{k}"]
             sk = ndcg_score(rels[None, :], scores[None, :], k=k)
             assert abs(mine - sk) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------
+# score-matrix consumers (criterion.py losses, rank-gap mining): oracle vs outputs of the unmodified
+# reference stored in tests/golden/losses.npz (tests/golden/make_golden_losses.py)
+# ----------------------------------------------------------------------------------------------
+LOSS_CASES = ["b32_n500_k10", "b32_n1000_k40_T05", "b5_n70_k40_T2", "b1_n12_k12"]
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_loss_oracle_matches_reference(name):
+    from oracle import loss_oracle as lo
+    z = np.load(U.GOLDEN / "losses.npz")
+    B, N, k, aux, _ = (int(v) for v in z[f"{name}/spec"])
+    T = float(z[f"{name}/T"])
+    s, t = z[f"{name}/s"], z[f"{name}/t"]
+    for key, (loss, grad) in {"listwise": lo.listwise_distillation_loss(s, t, k, T),
+                              "mse": lo.score_preserving_loss(s, t),
+                              "pairwise": lo.pairwise_distillation_loss(s, t)}.items():
+        np.testing.assert_allclose(loss, z[f"{name}/{key}_loss"], rtol=2e-5, err_msg=key)
+        ref_g = z[f"{name}/{key}_grad"]
+        np.testing.assert_allclose(grad, ref_g, rtol=2e-4, atol=2e-6 * np.abs(ref_g).max(), err_msg=key)
+    rg = lo.rank_gap(t, s, k, aux)
+    for key, ref_key in (("rank_t", "rank_t"), ("rank_s", "rank_s"), ("gap", "gap"), ("G", "G"),
+                         ("topk_idx", "topk_idx")):
+        np.testing.assert_array_equal(rg[key], z[f"{name}/{ref_key}"], err_msg=key)
+    # the hardest `aux` pages: same |gap| values in the same order (equal gaps may name another page)
+    gap = np.abs(z[f"{name}/gap"])
+    rows = np.arange(B)[:, None]
+    np.testing.assert_array_equal(gap[rows, rg["aux_doc_idx"]], gap[rows, z[f"{name}/aux_doc_idx_q"]])
+
+
+def test_listwise_oracle_rejects_k_above_n():
+    from oracle import loss_oracle as lo
+    with pytest.raises(ValueError):
+        lo.listwise_distillation_loss(np.zeros((2, 5)), np.zeros((2, 5)), k=6)
