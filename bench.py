@@ -198,6 +198,8 @@ def workload_config(args, n_gpus):
         "queries": args.queries, "pages_per_gpu": args.pages, "pages_total": args.pages * n_gpus,
         "tokens_per_page": LP_VALID, "token_slots_per_page": LP_SLOTS, "query_tokens": LQ, "dim": D,
         "top_k": TOPK, "parallelism": f"page-sharded x{n_gpus}, queries replicated",
+        "exchange": "none (1 GPU)" if n_gpus == 1 else
+                    ("ncclAllGather + merge" if args.exchange == "nccl" else "one-kernel peer-memory exchange + merge"),
         "l2": f"inputs larger than L2 ({args.pages * LP_SLOTS * D * 2 / 1e9:.1f} GB corpus per GPU vs 126 MB)",
     }
 
@@ -213,6 +215,8 @@ def main():
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--no-extras", action="store_true", help="skip the single-query / 64-query side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="candidate exchange at N > 1: ncclAllGather + merge, or the one-kernel peer-memory exchange")
     ap.add_argument("--corpus-1m", action="store_true", help="also run the 1M-page top-10 QPS measurement at 2 GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -242,7 +246,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         evdr.init_nccl_comm(dev)
+        if args.exchange == "peer":
+            evdr.init_peer_exchange(dev, max_candidates=max(args.queries, 64) * TOPK)
     n_gpus = world
+    xmode = args.exchange if world > 1 else "nccl"
     peaks = load_peaks()
 
     # ---- synthetic shard, generated on the device (never staged through host memory)
@@ -257,14 +264,14 @@ def main():
     Q = Qh.to(dev)
     qm = qmh.to(dev)
     scores = torch.empty((nq, npg), dtype=torch.float32, device=dev)
-    search = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode="nccl")
+    search = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode=xmode)
 
     def step():
         Qb, qm32 = evdr.pack_queries(Q, qm)                          # 1 launch  (pack_queries_kernel)
         pk.score_packed(Qb, qm32, out=scores)                        # 1 launch  (maxsim_tc_kernel)
         return search.topk(scores, TOPK)                             # 1 launch  (topk_select_kernel); N > 1:
                                                                      # + unpack_gathered + merge (+ NCCL's own)
-    launches_per_step = 3 if n_gpus == 1 else 5
+    launches_per_step = 3 if n_gpus == 1 else (4 if xmode == "peer" else 5)
 
     def barrier():
         if world > 1:
@@ -335,13 +342,21 @@ def main():
             extras = side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus)
         except Exception as e:  # side numbers must never lose the headline line
             extras = {"error": repr(e)}
+        # everything-on-the-host variant of e2e (N = 1): the page corpus itself starts in pinned host
+        # memory every step and is streamed through the GPU behind the scoring (HostCorpus)
+        if n_gpus == 1:
+            try:
+                extras["e2e_host_corpus"] = host_corpus_e2e(evdr, torch, corpus, Qh, qmh, host_scores, dev, timed,
+                                                            args.steps, pairs_per_step)
+            except Exception as e:
+                extras["e2e_host_corpus"] = {"error": repr(e)}
         # BASELINE.json configs[3]: top-10 QPS on a 1 M-page corpus sharded over the box (needs the
         # memory of >= 4 GPUs at 100k pages already resident; 2 GPUs only with --corpus-1m)
         if n_gpus >= 4 or (n_gpus >= 2 and args.corpus_1m):
             try:
                 del pk, corpus, pmask, scores, host_scores
                 torch.cuda.empty_cache()
-                extras["corpus_1m"] = corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed)
+                extras["corpus_1m"] = corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed, xmode)
             except Exception as e:
                 extras["corpus_1m"] = {"error": repr(e)}
 
@@ -367,7 +382,7 @@ def main():
         dist.destroy_process_group()
 
 
-def corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed):
+def corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed, xmode="nccl"):
     """Top-10 QPS on a 1,000,000-page corpus (266 GB bf16) sharded by page range over the GPUs of the
     box: streaming single-query and 64-query batches, local scan + top-10, NCCL all-gather, merge."""
     total = 1_000_000
@@ -375,8 +390,8 @@ def corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed):
     npg = hi - lo
     corpus = evdr.synth.make_uniform_corpus(npg, LP_SLOTS, device=dev, seed=4242 + 1000 * rank)
     pk = evdr.PackedPages.from_uniform_tokens(corpus, page_offset=lo)
-    search = evdr.ShardedSearch((lo, hi), mode="nccl")
-    out = {"pages_total": total, "pages_per_gpu": npg, "corpus_gb_per_gpu": npg * LP_SLOTS * D * 2 / 1e9}
+    search = evdr.ShardedSearch((lo, hi), mode=xmode)
+    out = {"exchange": xmode, "pages_total": total, "pages_per_gpu": npg, "corpus_gb_per_gpu": npg * LP_SLOTS * D * 2 / 1e9}
     for nq in (1, 64):
         g = torch.Generator().manual_seed(70 + nq)
         Q = torch.nn.functional.normalize(torch.randn(nq, LQ, D, generator=g), dim=-1).to(dev)
@@ -399,6 +414,37 @@ def corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed):
             rec["frac_of_bf16_burst_peak"] = tf / peaks["bf16_tflops"]
         out[f"q{nq}"] = rec
     return out
+
+
+def host_corpus_e2e(evdr, torch, corpus, Qh, qmh, host_scores, dev, timed, steps, pairs_per_step):
+    """The same step with NOTHING resident: queries AND the whole page corpus are read from pinned host
+    memory inside the timed region (chunked host->device copies on a copy stream, overlapped with the
+    scoring of the previous chunk), the (nq, np) score matrix is read back."""
+    need = corpus.numel() * 2
+    avail = 0
+    with open("/proc/meminfo") as f:
+        for ln in f:
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    if avail < 2 * need + (8 << 30):
+        return {"skipped": f"host has {avail / 1e9:.0f} GB available, needs {2 * need / 1e9:.0f} GB headroom to pin the corpus"}
+    host = torch.empty(corpus.shape, dtype=corpus.dtype, pin_memory=True)
+    host.copy_(corpus)
+    torch.cuda.synchronize()
+    hc = evdr.HostCorpus(host, dev)
+
+    def step():
+        Qd = Qh.to(dev, non_blocking=True)
+        qd = qmh.to(dev, non_blocking=True)
+        host_scores.copy_(hc.score(Qd, qd), non_blocking=True)
+
+    ms = timed(step, max(3, steps), 2)
+    h2d = need + Qh.numel() * 4 + qmh.numel()
+    return {"value": pairs_per_step / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": host_scores.numel() * 4, "h2d_gbs": h2d / (ms * 1e-3) / 1e9,
+            "pages_per_chunk": hc.ppc,
+            "call": "HostCorpus(pinned bf16 corpus).score(Q, qmask): corpus, queries and masks start in pinned "
+                    "host memory every step; scores are read back"}
 
 
 def side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus):

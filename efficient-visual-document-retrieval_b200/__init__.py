@@ -12,14 +12,14 @@ package ``evdr_b200`` at the repository root.
 """
 from . import _lib
 from . import corpus, losses, mining, normalize, retrieval, sharded, synth, topk
-from .corpus import PackedPages, pack_queries
+from .corpus import HostCorpus, PackedPages, pack_queries
 from .losses import (liscore_losses, listwise_distillation_loss, pairwise_distillation_loss, rank_gap,
                      score_preserving_loss)
 from .mining import hard_token_argmax, hard_tokens
 from .normalize import l2_normalize, l2_normalize_masked
 from .retrieval import (BaseVisualRetrieverProcessor, CustomRetrievalEvaluator, maxsim_exact,
                         score_multi_vector_masked)
-from .sharded import ShardedSearch, init_nccl_comm, partition_pages
+from .sharded import ShardedSearch, init_nccl_comm, init_peer_exchange, partition_pages
 from .topk import retrieval_metrics, topk as top_k, topk_merge, topk_metrics
 
 __version__ = "0.1.0"

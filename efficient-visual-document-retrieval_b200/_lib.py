@@ -52,6 +52,10 @@ _SIGNATURES = {
     "evdr_comm_init": ([_vp, _vp, _i, _i], _i),
     "evdr_comm_world": ([_vp], _i),
     "evdr_sharded_topk": ([_vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp], _i),
+    "evdr_peer_region_init": ([_vp, _i, _i, _i, _vp], _i),
+    "evdr_peer_connect": ([_vp, _vp], _i),
+    "evdr_peer_world": ([_vp], _i),
+    "evdr_peer_sharded_topk": ([_vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp], _i),
     "evdr_l2norm_fwd": ([_vp, _vp, _vp, _i64, _i, _vp, _vp], _i),
     "evdr_l2norm_bwd": ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp], _i),
     "evdr_rank_gap": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),

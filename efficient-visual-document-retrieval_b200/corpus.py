@@ -221,3 +221,73 @@ class PackedPages:
     @property
     def nbytes(self) -> int:
         return self.tokens.numel() * 2 + self.chunk_off.numel() * 4
+
+
+class HostCorpus:
+    """A uniform bf16 corpus that lives in PINNED HOST memory and is streamed through the GPU: the page
+    range is cut into chunks, chunk i+1 travels host->device on a copy stream into one of two staging
+    buffers while the tensor-core kernel scores chunk i on the caller's stream, and every chunk's
+    scores land directly in their columns of the (nq, np) result (the kernel takes a leading
+    dimension).  For query batches large enough to be tensor-bound (about 900 queries at PCIe Gen5
+    x16: 266 KB per page vs 8.4 MFLOP per pair) the copy hides behind the scoring, i.e. a corpus that
+    does not fit -- or has not been loaded into -- HBM is scored at the resident rate.
+
+    tokens_host: (np, L, 128) bf16, pinned, L % 16 == 0, every slot a valid token (filler slots hold a
+    duplicate of one of the page's tokens, like PackedPages).  The reference keeps the corpus on the
+    device (mainv2_iter_listwise.py:96); this class is the end-to-end "everything starts on the host"
+    measurement of bench.py and the route for corpora beyond 180 GB per GPU.
+    """
+
+    def __init__(self, tokens_host: torch.Tensor, device, pages_per_chunk: int = 0, page_offset: int = 0):
+        if tokens_host.is_cuda or not tokens_host.is_pinned():
+            raise ValueError("HostCorpus needs a pinned host tensor")
+        npg, L, d = tokens_host.shape
+        if tokens_host.dtype != torch.bfloat16 or d != TC_DIM or L % CHUNK != 0 or not tokens_host.is_contiguous():
+            raise ValueError("HostCorpus needs contiguous bf16 (np, L%16==0, 128)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.EvdrError("HostCorpus scores on the GPU: this package has no CPU fallback")
+        self.host = tokens_host
+        self.n_pages, self.L = npg, L
+        self.page_offset = int(page_offset)
+        if pages_per_chunk <= 0:                       # ~2 GiB per staging buffer
+            pages_per_chunk = max(1, (2 << 30) // (L * d * 2))
+        self.ppc = min(int(pages_per_chunk), npg)
+        self._stage = [torch.empty((self.ppc, L, d), dtype=torch.bfloat16, device=self.device) for _ in range(2)]
+        cpp = L // CHUNK
+        self._chunk_off = torch.arange(0, (self.ppc + 1) * cpp, cpp, dtype=torch.int32, device=self.device)
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._loaded = [torch.cuda.Event() for _ in range(2)]
+        self._consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def score(self, Q: torch.Tensor, qmask: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """MaxSim of (nq, lq <= 128, 128) queries (device) against the host corpus -> fp32 (nq, np) on device."""
+        Qs, ms, G = split_long_queries(Q, qmask)
+        Qb, qm32 = pack_queries(Qs, ms)
+        rows = Qb.shape[0]
+        dev = self.device
+        full = torch.empty((rows, self.n_pages), dtype=torch.float32, device=dev) if (out is None or G > 1) else out
+        main = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        n_chunks = (self.n_pages + self.ppc - 1) // self.ppc
+        # the staging buffers may still be read by a previous call on this stream
+        cs.wait_stream(main)
+        for i in range(n_chunks):
+            b = i & 1
+            c0, c1 = i * self.ppc, min(self.n_pages, (i + 1) * self.ppc)
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(self._consumed[b])       # the kernel of chunk i-2 is done with buffer b
+                self._stage[b][: c1 - c0].copy_(self.host[c0:c1], non_blocking=True)
+                self._loaded[b].record(cs)
+            main.wait_event(self._loaded[b])
+            n = c1 - c0
+            pk = PackedPages(self._stage[b][:n].view(n * self.L, TC_DIM), self._chunk_off[: n + 1], n,
+                             n * (self.L // CHUNK), self.page_offset + c0)
+            pk.score_packed(Qb, qm32, out=full[:, c0:c1])
+            self._consumed[b].record(main)
+        res = group_sum(full, G)
+        if out is not None and res is not out:
+            out.copy_(res)
+            return out
+        return res

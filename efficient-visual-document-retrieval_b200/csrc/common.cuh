@@ -68,6 +68,14 @@ struct evdr_handle {
   // multi-GPU
   void* nccl_comm;  // ncclComm_t
   int rank, world;
+  // peer-memory candidate exchange over NVLink (sharded.cu): this rank's exchange region, every rank's
+  // region as seen from here (device array of `world` pointers; entry `rank` is the local one), the
+  // capacity of one slot in candidates and the call sequence number (epoch = seq & 1)
+  unsigned char* peer_local;
+  unsigned char** peer_ptrs_dev;
+  void* peer_opened[16];
+  int peer_world, peer_rank, peer_cap;
+  unsigned peer_seq;
 };
 
 #define EVDR_REQUIRE_HANDLE(h)                                                        \

@@ -65,14 +65,199 @@ __global__ void unpack_gathered_kernel(const unsigned char* __restrict__ blob, i
   ci[o] = id[j];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchange: merge + all-gather in ONE kernel over NVLink / NVSwitch P2P stores.
+//
+// Every rank owns an exchange region (cudaMalloc, shared through CUDA IPC):
+//     [2 epochs][world source ranks][cap candidates] x (int64 id, fp32 score)  +  flags [2][world][PEER_MAXQ]
+// Per query q (CTA-strided): the CTA copies this rank's local top-k of q into the slot
+// (epoch, my rank) of EVERY rank's region with plain remote stores, fences at system scope and
+// releases the per-(source rank, query) flag on every rank; it then acquires the `world` flags of q in
+// its own region and merges the world * k candidates (score desc, id asc) straight into the result.
+// No NCCL launch, no unpack pass; the transfer of query q overlaps the merge of the queries before it.
+// Two epochs (call parity) suffice: a rank can only start call n+2 after every peer has pushed call
+// n+1, i.e. after that peer's call-n kernel -- the last reader of the epoch being overwritten -- is
+// complete (stream order).  Waits are bounded: a missing peer traps instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+constexpr int PEER_MAXQ = 4096;           // queries per call
+constexpr int PEER_MAX_WORLD = 16;
+constexpr int PEER_THREADS = 256;
+
+__host__ __device__ inline size_t peer_slot_bytes(size_t cap) { return cap * 12; }   // ids then scores
+__host__ __device__ inline size_t peer_data_bytes(int world, size_t cap) {
+  return ((2 * (size_t)world * peer_slot_bytes(cap) + 127) / 128) * 128;
+}
+__host__ __device__ inline size_t peer_region_bytes(int world, size_t cap) {
+  return peer_data_bytes(world, cap) + sizeof(unsigned) * 2 * (size_t)world * PEER_MAXQ;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(PEER_THREADS)
+exchange_merge_kernel(unsigned char* const* __restrict__ regions, int world, int rank, int cap,
+                      unsigned seq, const float* __restrict__ loc_s, const long long* __restrict__ loc_i,
+                      int nq, int k, float* __restrict__ top_s, long long* __restrict__ top_i) {
+  extern __shared__ unsigned char sm_raw[];
+  long long* cid = reinterpret_cast<long long*>(sm_raw);                  // [world * k]
+  float* csc = reinterpret_cast<float*>(cid + (size_t)world * k);         // [world * k]
+  const int epoch = seq & 1u;
+  const size_t slot = peer_slot_bytes(cap);
+  const size_t data = peer_data_bytes(world, cap);
+  const int per = nq * k;
+  const int n = world * k;
+  for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+    // ---- push: this rank's k candidates of query q into slot (epoch, rank) of every region
+    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+      const int r = i / k, t = i % k;
+      unsigned char* base = regions[r] + ((size_t)epoch * world + rank) * slot;
+      reinterpret_cast<long long*>(base)[q * k + t] = loc_i[(size_t)q * k + t];
+      reinterpret_cast<float*>(base + (size_t)per * 8)[q * k + t] = loc_s[(size_t)q * k + t];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+      unsigned* fl = reinterpret_cast<unsigned*>(regions[threadIdx.x] + data);
+      st_release_sys(fl + ((size_t)epoch * world + rank) * PEER_MAXQ + q, seq);
+      // ---- wait for source rank threadIdx.x to have delivered query q here
+      const unsigned* mine = reinterpret_cast<const unsigned*>(regions[rank] + data) +
+                             ((size_t)epoch * world + threadIdx.x) * PEER_MAXQ + q;
+      unsigned spins = 0;
+      while (ld_acquire_sys(mine) != seq) {
+        __nanosleep(256);
+        if (++spins > (1u << 25)) __trap();        // ~30 s: a peer never arrived
+      }
+    }
+    __syncthreads();
+    // ---- gather the world * k candidates of q (remote writes: bypass L1)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int r = i / k, t = i % k;
+      const unsigned char* base = regions[rank] + ((size_t)epoch * world + r) * slot;
+      cid[i] = __ldcv(reinterpret_cast<const long long*>(base) + q * k + t);
+      csc[i] = __ldcv(reinterpret_cast<const float*>(base + (size_t)per * 8) + q * k + t);
+    }
+    __syncthreads();
+    // ---- merge: position = number of better candidates (score desc, id asc; padding (-inf, -1) last)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float s = csc[i];
+      const long long id = cid[i];
+      const bool pad = id < 0;
+      int pos = 0;
+      for (int j = 0; j < n; ++j) {
+        const float os = csc[j];
+        const long long oid = cid[j];
+        const bool opad = oid < 0;
+        const bool better = pad ? (!opad || j < i)
+                                : (!opad && ((os > s) || (os == s && (oid < id || (oid == id && j < i)))));
+        pos += better;
+      }
+      if (pos < k) {
+        top_s[(size_t)q * k + pos] = pad ? -INFINITY : s;
+        top_i[(size_t)q * k + pos] = pad ? -1 : id;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace evdr
 
 using namespace evdr;
 
 extern "C" {
 
+int evdr_peer_region_init(evdr_handle* h, int rank, int world, int max_candidates, void* ipc_handle_out) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(ipc_handle_out && world >= 1 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world &&
+                 max_candidates >= 1, "evdr_peer_region_init: bad arguments");
+  if (h->peer_local) return set_error(EVDR_ERR_STATE, "evdr_peer_region_init: already initialised");
+  static_assert(sizeof(cudaIpcMemHandle_t) == EVDR_IPC_HANDLE_BYTES, "IPC handle size");
+  max_candidates += max_candidates & 1;          // slots stay 8-byte aligned
+  const size_t bytes = peer_region_bytes(world, (size_t)max_candidates);
+  unsigned char* reg = nullptr;
+  EVDR_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg), bytes));
+  EVDR_CUDA(cudaMemset(reg, 0, bytes));
+  cudaIpcMemHandle_t ipc;
+  cudaError_t e = cudaIpcGetMemHandle(&ipc, reg);
+  if (e != cudaSuccess) {
+    cudaFree(reg);
+    return set_error(EVDR_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+  h->peer_local = reg;
+  h->peer_rank = rank;
+  h->peer_world = world;
+  h->peer_cap = max_candidates;
+  h->peer_seq = 0;
+  return EVDR_OK;
+}
+
+int evdr_peer_connect(evdr_handle* h, const void* all_ipc_handles) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(all_ipc_handles, "evdr_peer_connect: null pointer");
+  if (!h->peer_local) return set_error(EVDR_ERR_STATE, "evdr_peer_connect before evdr_peer_region_init");
+  if (h->peer_ptrs_dev) return set_error(EVDR_ERR_STATE, "evdr_peer_connect: already connected");
+  unsigned char* ptrs[PEER_MAX_WORLD] = {};
+  for (int r = 0; r < h->peer_world; ++r) {
+    if (r == h->peer_rank) { ptrs[r] = h->peer_local; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, static_cast<const unsigned char*>(all_ipc_handles) + (size_t)r * sizeof(ipc), sizeof(ipc));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return set_error(EVDR_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s (GPUs without peer access?)",
+                       r, cudaGetErrorString(e));
+    h->peer_opened[r] = p;
+    ptrs[r] = static_cast<unsigned char*>(p);
+  }
+  EVDR_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->peer_ptrs_dev), sizeof(ptrs)));
+  EVDR_CUDA(cudaMemcpy(h->peer_ptrs_dev, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+  return EVDR_OK;
+}
+
+int evdr_peer_world(const evdr_handle* h) { return (h && h->peer_ptrs_dev) ? h->peer_world : 0; }
+
+int evdr_peer_sharded_topk(evdr_handle* h, const float* local_scores, int64_t ld, int nq, int np_local,
+                           int k, int64_t id_offset, float* top_scores, int64_t* top_ids, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(local_scores && top_scores && top_ids, "evdr_peer_sharded_topk: null pointer");
+  if (!h->peer_ptrs_dev) return set_error(EVDR_ERR_STATE, "evdr_peer_sharded_topk before evdr_peer_connect");
+  EVDR_CHECK_ARG(nq >= 1 && nq <= PEER_MAXQ && k >= 1 && (long long)nq * k <= h->peer_cap,
+                 "evdr_peer_sharded_topk: nq=%d x k=%d exceeds the exchange region (%d candidates, %d queries)",
+                 nq, k, h->peer_cap, PEER_MAXQ);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t per = (size_t)nq * k;
+  unsigned char* ws = nullptr;
+  EVDR_CUDA(cudaMallocAsync(&ws, per * 12 + 64, st));
+  int64_t* loc_i = reinterpret_cast<int64_t*>(ws);
+  float* loc_s = reinterpret_cast<float*>(ws + per * 8);
+  int rc = evdr_topk(h, local_scores, ld, nq, np_local, k, nullptr, id_offset, loc_s, loc_i, stream);
+  if (rc != EVDR_OK) { cudaFreeAsync(ws, st); return rc; }
+  const unsigned seq = ++h->peer_seq;
+  const int grid = nq < 2 * h->sm_count ? nq : 2 * h->sm_count;
+  const size_t smem = (size_t)h->peer_world * k * 12;
+  exchange_merge_kernel<<<grid, PEER_THREADS, smem, st>>>(
+      h->peer_ptrs_dev, h->peer_world, h->peer_rank, h->peer_cap, seq, loc_s,
+      reinterpret_cast<const long long*>(loc_i), nq, k, top_scores, reinterpret_cast<long long*>(top_ids));
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(ws, st);
+  if (le != cudaSuccess)
+    return set_error(EVDR_ERR_CUDA, "launch of exchange_merge_kernel failed: %s", cudaGetErrorString(le));
+  return EVDR_OK;
+}
+
 int evdr_destroy(evdr_handle* h) {
   if (!h) return EVDR_OK;
+  for (int r = 0; r < PEER_MAX_WORLD; ++r)
+    if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_opened[r]);
+  if (h->peer_ptrs_dev) cudaFree(h->peer_ptrs_dev);
+  if (h->peer_local) cudaFree(h->peer_local);
   if (h->nccl_comm) {
     NcclApi* api = nccl_api();
     if (api) api->CommDestroy(static_cast<nccl_comm_t>(h->nccl_comm));

@@ -2,7 +2,11 @@
 one box (one process per GPU), queries are replicated, every rank computes a local top-k and the
 candidates are merged after ONE all-gather.  There is no other data-path collective.
 
-Two exchange modes:
+Three exchange modes:
+* "peer": `evdr_peer_sharded_topk` -- local top-k, then ONE kernel that pushes the candidates into
+  every rank's exchange region with remote stores over NVLink (CUDA IPC peer memory), signals per-query
+  flags and merges as soon as all ranks' candidates of a query have landed; no NCCL on the data path
+  (set up with `init_peer_exchange`);
 * "nccl"  (default on CUDA): `evdr_sharded_topk` -- local top-k, ncclAllGather of nq*k (score, id)
   pairs on the caller's stream and the merge kernel, all inside libevdr.so;
 * "torchdist": the same three steps with the all-gather done by torch.distributed on whatever
@@ -49,6 +53,30 @@ def init_nccl_comm(device: torch.device, group=None) -> None:
     _lib.check(lib.evdr_comm_init(_lib.handle(device), C.cast(buf, C.c_void_p), rank, world), "evdr_comm_init")
 
 
+def init_peer_exchange(device: torch.device, group=None, max_candidates: int = 64 * 128) -> None:
+    """Set up libevdr's peer-memory exchange for this rank: allocate the exchange region, gather every
+    rank's CUDA IPC handle with torch.distributed (the plumbing) and open the peers' regions.  After this
+    ShardedSearch(mode="peer") needs no NCCL call on the data path.  `max_candidates` bounds nq * k per
+    search (default: 64 queries x top-128, or 819 queries x top-10)."""
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    h = _lib.handle(device)
+    if lib.evdr_peer_world(h) == world:
+        return
+    buf = (C.c_ubyte * 64)()
+    _lib.check(lib.evdr_peer_region_init(h, rank, world, int(max_candidates), C.cast(buf, C.c_void_p)),
+               "evdr_peer_region_init")
+    mine = torch.tensor(list(buf), dtype=torch.uint8)
+    backend = dist.get_backend(group)
+    mine = mine.to(device) if backend == "nccl" else mine
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+    blob = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+    _lib.check(lib.evdr_peer_connect(h, C.cast(blob, C.c_void_p)), "evdr_peer_connect")
+    dist.barrier(group=group)      # nobody pushes into a region before its owner has opened everyone
+
+
 class ShardedSearch:
     """Global top-k over per-rank score blocks.
 
@@ -73,7 +101,7 @@ class ShardedSearch:
         nq, n_local = local_scores.shape
         assert n_local == self.end - self.start, "score block does not match this rank's page range"
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        if self.mode == "nccl":
+        if self.mode in ("nccl", "peer"):
             dev = local_scores.device
             _lib.require_cuda(local_scores, "local_scores")
             top_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
@@ -81,9 +109,10 @@ class ShardedSearch:
             if local_scores.stride(1) != 1:
                 local_scores = local_scores.contiguous()
             lib = _lib.load()
-            _lib.check(lib.evdr_sharded_topk(_lib.handle(dev), local_scores.data_ptr(), local_scores.stride(0),
-                                             nq, n_local, k, self.start, top_s.data_ptr(), top_i.data_ptr(),
-                                             _lib.stream_ptr(dev)), "evdr_sharded_topk")
+            fn = lib.evdr_peer_sharded_topk if self.mode == "peer" else lib.evdr_sharded_topk
+            _lib.check(fn(_lib.handle(dev), local_scores.data_ptr(), local_scores.stride(0), nq, n_local, k,
+                          self.start, top_s.data_ptr(), top_i.data_ptr(), _lib.stream_ptr(dev)),
+                       "evdr_peer_sharded_topk" if self.mode == "peer" else "evdr_sharded_topk")
             return top_s, top_i
         loc_s, loc_i = self._local_topk(local_scores, k, self.start)
         if world == 1:

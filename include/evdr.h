@@ -249,6 +249,25 @@ EVDR_API int evdr_sharded_topk(evdr_handle* h, const float* local_scores_dev, in
                                int nq, int np_local, int k, int64_t id_offset,
                                float* top_scores_dev, int64_t* top_ids_dev, void* stream);
 
+/* Peer-memory exchange (no NCCL on the data path): every rank owns an exchange region shared through
+ * CUDA IPC; ONE kernel copies the local top-k of each query into all peers' regions with remote
+ * stores over NVLink, releases per-query flags, acquires the peers' flags and merges the world * k
+ * candidates into the result (same order as evdr_topk_merge: score descending, id ascending).
+ *   evdr_peer_region_init : allocate this rank's region for up to `max_candidates` = nq * k entries per
+ *                           call and return its 64-byte cudaIpcMemHandle_t;
+ *   evdr_peer_connect     : `all_ipc_handles` = world x 64 bytes in rank order (the host plumbing --
+ *                           torch.distributed -- gathers them); opens every peer's region;
+ *   evdr_peer_sharded_topk: collective, same arguments and result as evdr_sharded_topk.  nq <= 4096.
+ * Waits are bounded (~30 s): a rank that never arrives traps the kernel instead of hanging the GPU. */
+#define EVDR_IPC_HANDLE_BYTES 64
+EVDR_API int evdr_peer_region_init(evdr_handle* h, int rank, int world, int max_candidates,
+                                   void* ipc_handle_out_64B);
+EVDR_API int evdr_peer_connect(evdr_handle* h, const void* all_ipc_handles);
+EVDR_API int evdr_peer_world(const evdr_handle* h);
+EVDR_API int evdr_peer_sharded_topk(evdr_handle* h, const float* local_scores_dev, int64_t ld,
+                                    int nq, int np_local, int k, int64_t id_offset,
+                                    float* top_scores_dev, int64_t* top_ids_dev, void* stream);
+
 /* ------------------------------------------------------------------------
  * A4  fused mask * l2_normalize (utils/preprocess_data.py:8-9 applied as
  * mainv2_iter_listwise.py:280) and its backward, fp32:

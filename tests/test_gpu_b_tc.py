@@ -164,3 +164,23 @@ def test_long_queries_split_into_groups(evdr, cuda, lq):
     ref = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
     U.assert_scores_close(got.cpu().numpy(), ref.cpu().numpy())
     assert got.shape == (11, 120)
+
+
+@pytest.mark.parametrize("nq,ppc", [(5, 7), (40, 16), (3, 1000)])
+def test_host_corpus_streaming_equals_resident_scoring(evdr, cuda, nq, ppc):
+    """HostCorpus streams a pinned host corpus through two staging buffers while the kernel scores the
+    previous chunk: per-page results are bit-identical to scoring the resident corpus in one launch."""
+    npg, L = 53, 208
+    corpus = evdr.synth.make_uniform_corpus(npg, L, device=cuda, seed=9)
+    host = corpus.cpu().pin_memory()
+    g = torch.Generator(device=cuda).manual_seed(nq)
+    Q = torch.nn.functional.normalize(torch.randn(nq, 32, 128, generator=g, device=cuda), dim=-1)
+    qm = torch.rand(nq, 32, generator=g, device=cuda) > 0.1
+    want = evdr.PackedPages.from_uniform_tokens(corpus).score(Q, qm)
+    hc = evdr.HostCorpus(host, cuda, pages_per_chunk=ppc)
+    got = hc.score(Q, qm)
+    assert torch.equal(got, want)
+    out = torch.empty_like(want)
+    assert hc.score(Q, qm, out=out) is out and torch.equal(out, want)      # staging buffers reused
+    with pytest.raises(ValueError):
+        evdr.HostCorpus(corpus.cpu(), cuda)                                   # not pinned

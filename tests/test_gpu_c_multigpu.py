@@ -36,6 +36,20 @@ def _worker(rank, world, port, ret):
         ref_s, ref_i = evdr.top_k(full, k)
         ok = torch.equal(top_i, ref_i) and torch.allclose(top_s, ref_s, rtol=0, atol=1e-5)
         ok = ok and bool((top_i[:, 0].cpu() == rel).float().mean() > 0.9)
+        # the same search through the peer-memory exchange (one kernel, no NCCL on the data path):
+        # repeated calls alternate the two epochs of the exchange regions, query counts above the grid
+        # size exercise the CTA-strided loop
+        evdr.init_peer_exchange(dev, max_candidates=1200 * 10)
+        peer = evdr.ShardedSearch((lo, hi), mode="peer")
+        for _ in range(5):
+            ps, pi = peer.topk(local, k)
+            ok = ok and torch.equal(pi, top_i) and torch.equal(ps, top_s)
+        big = local.repeat(30, 1)[:1100]                      # 1100 query rows
+        ns, ni = evdr.ShardedSearch((lo, hi), mode="nccl").topk(big, k)
+        ps, pi = peer.topk(big, k)
+        ok = ok and torch.equal(pi, ni) and torch.equal(ps, ns)
+        ps, pi = peer.topk(local[:1], 3)
+        ok = ok and torch.equal(pi, top_i[:1, :3])
         gathered = [None] * world
         dist.all_gather_object(gathered, top_i.cpu().tolist())
         ok = ok and all(g == gathered[0] for g in gathered)
@@ -60,3 +74,25 @@ def test_sharded_search_nccl():
         p.join(300)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_peer_exchange_single_rank(evdr, cuda):
+    """world = 1: the exchange kernel pushes into its own region, waits on its own flags and merges --
+    the result must equal evdr_topk, including (-inf, -1) padding when k exceeds the page count."""
+    import ctypes as C
+    lib = evdr._lib.load()
+    h = evdr._lib.handle(cuda)
+    if lib.evdr_peer_world(h) == 0:
+        buf = (C.c_ubyte * 64)()
+        evdr._lib.check(lib.evdr_peer_region_init(h, 0, 1, 300 * 16, C.cast(buf, C.c_void_p)), "init")
+        evdr._lib.check(lib.evdr_peer_connect(h, C.cast(buf, C.c_void_p)), "connect")
+    assert lib.evdr_peer_world(h) == 1
+    g = torch.Generator(device=cuda).manual_seed(3)
+    for nq, npg, k in ((7, 500, 10), (300, 37, 16), (1, 5, 8)):
+        s = torch.randn(nq, npg, generator=g, device=cuda)
+        s[:, 1] = s[:, 0]                                      # ties resolve by id ascending
+        want_s, want_i = evdr.top_k(s, k, id_offset=100)
+        got_s, got_i = evdr.ShardedSearch((100, 100 + npg), mode="peer").topk(s, k)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+    with pytest.raises(ValueError):
+        evdr.ShardedSearch((0, 10), mode="peer").topk(torch.zeros(400, 10, device=cuda), 16)   # > region
