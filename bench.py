@@ -360,6 +360,9 @@ def main():
             except Exception as e:
                 extras["corpus_1m"] = {"error": repr(e)}
 
+    if isinstance(extras.get("e2e_host_corpus"), dict) and "value" in extras["e2e_host_corpus"]:
+        e2e["all_inputs_on_host"] = {k: extras["e2e_host_corpus"][k] for k in
+                                     ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:

@@ -17,7 +17,7 @@ from .losses import (liscore_losses, listwise_distillation_loss, pairwise_distil
                      score_preserving_loss)
 from .mining import hard_token_argmax, hard_tokens
 from .normalize import l2_normalize, l2_normalize_masked
-from .retrieval import (BaseVisualRetrieverProcessor, CustomRetrievalEvaluator, maxsim_exact,
+from .retrieval import (BaseVisualRetrieverProcessor, CustomRetrievalEvaluator, TeacherScoreTable, maxsim_exact,
                         score_multi_vector_masked)
 from .sharded import ShardedSearch, init_nccl_comm, init_peer_exchange, partition_pages
 from .topk import retrieval_metrics, topk as top_k, topk_merge, topk_metrics

@@ -260,15 +260,78 @@ bwd_dq_kernel(const float* __restrict__ gout, const TP* __restrict__ P,
   }
 }
 
-// Rescoring of tensor-core winners: one warp per (query-token row, page).  `am` holds the packed
-// slot chosen by the bf16 tcgen05 search (evdr_maxsim_packed_argmax); a slot that is a filler
-// (masked or beyond lp) is mapped back to the valid token it duplicates (nearest preceding valid
-// token, else the first valid one -- the pack rule), the token index replaces the slot in `am`
-// (the backward scatters through it) and the exact fp32 dot product goes to rowmax[c*R + r].
+// Rescoring of tensor-core winners.  `am` holds the packed slot chosen by the bf16 tcgen05 search
+// (evdr_maxsim_packed_argmax); a slot that is a filler (masked or beyond lp) is mapped back to the
+// valid token it duplicates (nearest preceding valid token, else the first valid one -- the pack
+// rule), the token index replaces the slot in `am` (the backward scatters through it) and the exact
+// fp32 dot product goes to rowmax[c*R + r].
+// One warp = one query-token row x 32 consecutive pages: the lanes keep the row's 128 components in
+// registers (4 each), every page costs one broadcast index load, one coalesced 512-byte token load
+// and 4 FMAs per lane, and the 32 per-page partial sums are reduced together by a 31-shuffle
+// transpose-reduction (lane j ends up with page j's dot product) instead of 32 five-step warp sums.
+// d == 128 only; other dims use rescore_generic_kernel.
 template <typename TQ, typename TP>
 __global__ void __launch_bounds__(256)
 rescore_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P, const uint8_t* __restrict__ pmask,
-               int32_t* __restrict__ am, int R, int lp, int d, float* __restrict__ rowmax) {
+               int32_t* __restrict__ am, int R, int np, int lp, float* __restrict__ rowmax) {
+  constexpr int d = 128;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int c0 = blockIdx.y * 32;
+  if (r >= R) return;
+  const float4 qv = load4(Q + (size_t)r * d + lane * 4);
+  float acc[32];
+  int t_mine = 0;
+  bool valid_mine = false;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = c0 + j;
+    float a = 0.f;
+    if (c < np) {                                          // warp-uniform
+      const uint8_t* mc = pmask + (size_t)c * lp;
+      int t = am[(size_t)c * R + r];
+      t = t < 0 ? 0 : (t >= lp ? lp - 1 : t);
+      if (!mc[t]) {                                        // filler slot: rare, warp-uniform
+        int u = t;
+        while (u >= 0 && !mc[u]) --u;
+        if (u < 0) { u = 0; while (u < lp && !mc[u]) ++u; }
+        t = u;                                             // == lp: page without valid tokens
+      }
+      const bool ok = t < lp;
+      if (ok) {
+        const float4 pv = load4(P + ((size_t)c * lp + t) * d + lane * 4);
+        a = fmaf(qv.x, pv.x, a);
+        a = fmaf(qv.y, pv.y, a);
+        a = fmaf(qv.z, pv.z, a);
+        a = fmaf(qv.w, pv.w, a);
+      }
+      if (lane == j) { t_mine = ok ? t : 0; valid_mine = ok; }
+    }
+    acc[j] = a;
+  }
+  // transpose-reduce: after step `o` lane l keeps the entries whose index has bit `o` equal to l's
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float mine = up ? acc[j + o] : acc[j];
+      const float give = up ? acc[j] : acc[j + o];
+      acc[j] = mine + __shfl_xor_sync(0xffffffffu, give, o);
+    }
+  }
+  const int c = c0 + lane;
+  if (c < np) {
+    am[(size_t)c * R + r] = t_mine;
+    rowmax[(size_t)c * R + r] = valid_mine ? acc[0] : kNegFill;   // :198 leaves -1e4 on empty pages
+  }
+}
+
+// any d % 4 == 0: one warp per (query-token row, page)
+template <typename TQ, typename TP>
+__global__ void __launch_bounds__(256)
+rescore_generic_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P, const uint8_t* __restrict__ pmask,
+                       int32_t* __restrict__ am, int R, int lp, int d, float* __restrict__ rowmax) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int c = blockIdx.y;
@@ -281,9 +344,9 @@ rescore_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P, const uint8_t
     int u = t;
     while (u >= 0 && !mc[u]) --u;
     if (u < 0) { u = 0; while (u < lp && !mc[u]) ++u; }
-    t = u;                                   // == lp: page without valid tokens
+    t = u;
   }
-  float v = kNegFill;                        // what the reference's masked_fill leaves (:198)
+  float v = kNegFill;
   if (t < lp) {
     const TQ* q = Q + (size_t)r * d;
     const TP* p = P + ((size_t)c * lp + t) * d;
@@ -308,9 +371,15 @@ rescore_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P, const uint8_t
 template <typename TQ, typename TP>
 static int launch_rescore(const void* Q, const void* P, const uint8_t* pmask, int32_t* am, int R, int np,
                           int lp, int d, float* rowmax, cudaStream_t st) {
-  dim3 grid((R + 7) / 8, np);
-  rescore_kernel<TQ, TP><<<grid, 256, 0, st>>>(static_cast<const TQ*>(Q), static_cast<const TP*>(P), pmask,
-                                                am, R, lp, d, rowmax);
+  if (d == 128) {
+    dim3 grid((R + 7) / 8, (np + 31) / 32);
+    rescore_kernel<TQ, TP><<<grid, 256, 0, st>>>(static_cast<const TQ*>(Q), static_cast<const TP*>(P), pmask,
+                                                  am, R, np, lp, rowmax);
+  } else {
+    dim3 grid((R + 7) / 8, np);
+    rescore_generic_kernel<TQ, TP><<<grid, 256, 0, st>>>(static_cast<const TQ*>(Q), static_cast<const TP*>(P),
+                                                          pmask, am, R, lp, d, rowmax);
+  }
   EVDR_LAUNCH_CHECK("rescore_kernel");
   return EVDR_OK;
 }

@@ -27,7 +27,7 @@ from .topk import retrieval_metrics, topk, topk_metrics
 
 __all__ = [
     "score_multi_vector_masked", "BaseVisualRetrieverProcessor", "CustomRetrievalEvaluator",
-    "get_torch_device", "left_padding", "maxsim_exact",
+    "get_torch_device", "left_padding", "maxsim_exact", "TeacherScoreTable",
 ]
 
 # rowmax scratch of the exact path is nq*lq*np floats; pages are processed in blocks that keep it
@@ -132,6 +132,17 @@ class _MaxSimRescoreFn(torch.autograd.Function):
         lib = _lib.load()
         h = _lib.handle(dev)
         st = _lib.stream_ptr(dev)
+        R = nq * lq
+        if 4 * R * npg <= _EXACT_WS_BYTES:
+            # one library call (evdr_maxsim_train_fwd): both packs, the search, the rescoring and the sum
+            am = torch.empty((npg, R), dtype=torch.int32, device=dev)
+            out = torch.empty((nq, npg), dtype=torch.float32, device=dev)
+            _lib.check(lib.evdr_maxsim_train_fwd(h, Q.data_ptr(), _lib.dtype_code(Q), P.data_ptr(), _lib.dtype_code(P),
+                                                 qm.data_ptr(), pm.data_ptr(), nq, npg, lq, lp, d, am.data_ptr(),
+                                                 out.data_ptr(), st), "evdr_maxsim_train_fwd")
+            ctx.save_for_backward(Q, P, qm, pm, am)
+            return out
+        # larger problems: the same steps composed here, the rescoring in page blocks
         # bf16x3 split operands: the search runs at ~fp32 accuracy, so the winners are the reference's.
         # Queries of 33..128 tokens arrive zero-padded to a multiple of 32 (score_multi_vector_masked) and
         # are searched as nq*G rows of 32 tokens: row-major (nq, G*32) IS (nq*G, 32), so the argmax table
@@ -270,6 +281,33 @@ def score_multi_vector_masked(
         return _MaxSimRescoreFn.apply(Qf, _float_operand(P), qm8, _mask_u8(pmask))
     with torch.no_grad():
         return _packed_for(P.detach(), pmask).score(Q.detach(), qmask)   # lq > 32: scored as 32-token groups
+
+
+class TeacherScoreTable:
+    """One-shot teacher scores.  The teacher pages are frozen and the pseudo-query
+    set is fixed, yet every step of the reference recomputes ``score_multi_vector_masked(Qb,
+    P_teacher_norm, qmb, pmask_teacher)`` under no_grad (mainv2_iter_listwise.py:283-284) -- each row
+    30 times over 30 epochs, always on the expensive 1030-token pages.  Scoring ALL queries against
+    the teacher once is a single tensor-core-bound call (25 000 queries x 1000 pages: ~0.15 s) whose
+    (Nq, Np) fp32 table is 100 MB; a training step then gathers its rows by dataset index.
+
+        table = TeacherScoreTable(Q_all, qmask_all, P_teacher_norm, pmask_teacher)
+        sc_t = table[batch_indices]          # (B, Np) fp32, == score_multi_vector_masked(Q_all[idx], ...)
+    """
+
+    def __init__(self, Q_all: torch.Tensor, qmask_all: torch.Tensor, P_teacher: torch.Tensor,
+                 pmask_teacher: torch.Tensor, query_block: int = 8192):
+        with torch.no_grad():
+            rows = [score_multi_vector_masked(Q_all[i:i + query_block], P_teacher, qmask_all[i:i + query_block],
+                                              pmask_teacher) for i in range(0, Q_all.shape[0], query_block)]
+        self.scores = rows[0] if len(rows) == 1 else torch.cat(rows, dim=0)
+
+    def __getitem__(self, idx) -> torch.Tensor:
+        idx = torch.as_tensor(idx, device=self.scores.device)
+        return self.scores.index_select(0, idx.reshape(-1).to(torch.int64))
+
+    def __len__(self) -> int:
+        return self.scores.shape[0]
 
 
 # ---------------------------------------------------------------------------

@@ -187,6 +187,17 @@ EVDR_API int evdr_maxsim_rescore(evdr_handle* h,
                                  int32_t* argmax_dev, int nq, int np, int lq, int lp, int d,
                                  float* rowmax_ws_dev, float* out_dev, void* stream);
 
+/* The forward of a gradient call in ONE library call: evdr_pack_queries(k_blocks=3) + evdr_pack_plan +
+ * evdr_pack_pages(k_blocks=3) + evdr_maxsim_packed_argmax + evdr_maxsim_rescore on a stream-ordered
+ * workspace (the student tensor changes every step, mainv2_iter_listwise.py:280,287, so nothing can be
+ * cached and the host-side issue time is paid per step).  Q (nq, lq, 128) with lq <= 32 or lq in
+ * {64, 96, 128} (zero-padded, masked); argmax_dev int32 [np, nq*lq] receives the winning page-token
+ * indices for evdr_maxsim_bwd; out_dev fp32 [nq, np]. */
+EVDR_API int evdr_maxsim_train_fwd(evdr_handle* h, const void* Q_dev, int q_dtype, const void* P_dev,
+                                   int p_dtype, const uint8_t* qmask_dev, const uint8_t* pmask_dev,
+                                   int nq, int np, int lq, int lp, int d, int32_t* argmax_dev,
+                                   float* out_dev, void* stream);
+
 /* A8  hard-token mining (mainv3_iter_liscore_QA_hardtoken.py:398-425): for every (query q, page
  * doc_idx[q, a]) the index of the VALID page token m maximising max_{valid n} <Q[q,n], P[c,m]> (the
  * column-max variant of MaxSim; ties -> lowest index).  Replaces a Python double loop with a host

@@ -130,10 +130,15 @@ def test_config1_docvqa_end_to_end(evdr, cuda):
     assert 0.3 < want["NDCG"]["NDCG@5"] < 1.0, want["NDCG"]
 
 
-def test_rescore_path_vs_exact_on_fp32_operands(evdr, cuda):
+@pytest.mark.parametrize("composed", [False, True])
+def test_rescore_path_vs_exact_on_fp32_operands(evdr, cuda, composed, monkeypatch):
     """Gradient calls run a bf16x3 (near-fp32) tensor-core search and rescore the winners in fp32.  On
     operands that are NOT bf16-representable the result must equal the exact fp32 path: same scores,
-    same winners (up to ties at the 1e-6 level), same gradients."""
+    same winners (up to ties at the 1e-6 level), same gradients.  composed=True forces the path for
+    problems beyond one evdr_maxsim_train_fwd call (steps issued from Python, rescoring in page blocks)."""
+    if composed:
+        import evdr_b200.retrieval as R
+        monkeypatch.setattr(R, "_EXACT_WS_BYTES", 1 << 19)
     g = torch.Generator(device=cuda).manual_seed(5)
     npg, ls, nq = 300, 103, 32
     P = torch.randn(npg, ls, 128, generator=g, device=cuda)
@@ -237,3 +242,18 @@ def test_hard_token_mining_matches_reference_loop(evdr, cuda):
     toks = evdr.hard_tokens(Q, qm, P, pm, doc_idx)
     assert toks.shape == (128, 1, 128)
     assert torch.equal(toks[5, 0], P[doc_idx.reshape(-1)[5], got.reshape(-1)[5]])
+
+
+def test_teacher_score_table_rows_equal_per_batch_calls(evdr, cuda):
+    """scoring every pseudo-query against the frozen teacher once and gathering rows
+    by dataset index gives the teacher scores of the per-step call of mainv2_iter_listwise.py:283-284
+    (same products and maxima; the 32-token sum may be ordered differently between kernel flavours)."""
+    P, pm = evdr.synth.make_pages(150, 333, seed=21, device=cuda, n_holes=4, empty_frac=0.02, min_len=50)
+    Q, qm, _ = evdr.synth.make_queries(P, pm, 300, 32, seed=22, sigma=2.0, min_len=6, drop=0.1)
+    table = evdr.TeacherScoreTable(Q, qm, P, pm, query_block=128)
+    assert len(table) == 300
+    idx = torch.tensor([5, 299, 0, 5, 128, 127], device=cuda)
+    with torch.no_grad():
+        want = evdr.score_multi_vector_masked(Q[idx], P, qm[idx], pm, 32)
+    torch.testing.assert_close(table[idx], want, rtol=0, atol=2e-5)
+    torch.testing.assert_close(table[[7]], evdr.score_multi_vector_masked(Q[7:8], P, qm[7:8], pm), rtol=0, atol=2e-5)
