@@ -220,7 +220,10 @@ metrics_kernel(const long long* __restrict__ top_ids, int kmax, int nq, const Me
 
 static int pick_nsplit(const evdr_handle* h, int nq, int n) {
   int want = (2 * h->sm_count + nq - 1) / nq;          // fill the GPU twice over
-  int cap = (n + 4095) / 4096;                          // >= 4096 columns per CTA
+  // >= 1024 columns per CTA: a warp's scan is a chain of dependent 32-column loads, so a single-query
+  // search over 100k pages wants ~100 short chains rather than 25 long ones (the second stage merges
+  // nsplit * k candidates in one CTA either way)
+  int cap = (n + 1023) / 1024;
   int ns = want < cap ? want : cap;
   return ns < 1 ? 1 : ns;
 }
