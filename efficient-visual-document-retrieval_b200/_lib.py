@@ -53,6 +53,7 @@ _SIGNATURES = {
     "evdr_comm_init": ([_vp, _vp, _i, _i], _i),
     "evdr_comm_world": ([_vp], _i),
     "evdr_sharded_topk": ([_vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp], _i),
+    "evdr_allgather_score_rows": ([_vp, _vp, _i64, _i, _i, _vp, _i64, _vp], _i),
     "evdr_peer_region_init": ([_vp, _i, _i, _i, _vp], _i),
     "evdr_peer_connect": ([_vp, _vp], _i),
     "evdr_peer_world": ([_vp], _i),

@@ -65,6 +65,32 @@ __global__ void unpack_gathered_kernel(const unsigned char* __restrict__ blob, i
   ci[o] = id[j];
 }
 
+// score column blocks for the training collective: pages are partitioned contiguously (first
+// np_total % world ranks own one page more), NCCL wants equal counts, so blocks travel padded to cmax
+// columns and are laid out by page offset on arrival
+__host__ __device__ inline int part_count(int n, int world, int r) { return n / world + (r < n % world ? 1 : 0); }
+__host__ __device__ inline int part_start(int n, int world, int r) {
+  return r * (n / world) + (r < n % world ? r : n % world);
+}
+
+__global__ void pad_block_kernel(const float* __restrict__ local, long long ld, int B, int cnt, int cmax,
+                                 float* __restrict__ send) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * cmax) return;
+  const int b = (int)(i / cmax), j = (int)(i % cmax);
+  send[i] = j < cnt ? local[(size_t)b * ld + j] : 0.f;
+}
+
+__global__ void place_blocks_kernel(const float* __restrict__ recv, int world, int B, int np_total, int cmax,
+                                    float* __restrict__ out, long long out_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)world * B * cmax) return;
+  const int j = (int)(i % cmax);
+  const int b = (int)((i / cmax) % B);
+  const int r = (int)(i / ((long long)cmax * B));
+  if (j < part_count(np_total, world, r)) out[(size_t)b * out_ld + part_start(np_total, world, r) + j] = recv[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Peer-memory exchange: merge + all-gather in ONE kernel over NVLink / NVSwitch P2P stores.
 //
@@ -249,6 +275,44 @@ int evdr_peer_sharded_topk(evdr_handle* h, const float* local_scores, int64_t ld
   cudaFreeAsync(ws, st);
   if (le != cudaSuccess)
     return set_error(EVDR_ERR_CUDA, "launch of exchange_merge_kernel failed: %s", cudaGetErrorString(le));
+  return EVDR_OK;
+}
+
+int evdr_allgather_score_rows(evdr_handle* h, const float* local_scores, int64_t ld, int B, int np_total,
+                              float* out, int64_t out_ld, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(local_scores && out && B >= 1 && np_total >= 1 && out_ld >= np_total,
+                 "evdr_allgather_score_rows: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int world = h->nccl_comm ? h->world : 1, rank = h->nccl_comm ? h->rank : 0;
+  const int cnt = part_count(np_total, world, rank);
+  EVDR_CHECK_ARG(ld >= cnt, "evdr_allgather_score_rows: ld=%lld < this rank's %d pages", (long long)ld, cnt);
+  if (world == 1) {
+    EVDR_CUDA(cudaMemcpy2DAsync(out, out_ld * sizeof(float), local_scores, ld * sizeof(float),
+                                (size_t)np_total * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    return EVDR_OK;
+  }
+  NcclApi* api = nccl_api();
+  if (!api) return set_error(EVDR_ERR_NCCL, "libnccl.so.2 not loadable");
+  const int cmax = part_count(np_total, world, 0);
+  const size_t blk = (size_t)B * cmax;
+  float* ws = nullptr;
+  EVDR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), sizeof(float) * blk * ((size_t)world + 1), st));
+  float* send = ws;
+  float* recv = ws + blk;
+  pad_block_kernel<<<(unsigned)((blk + 255) / 256), 256, 0, st>>>(local_scores, ld, B, cnt, cmax, send);
+  nccl_result_t r = api->AllGather(send, recv, blk * sizeof(float), kNcclChar,
+                                   static_cast<nccl_comm_t>(h->nccl_comm), st);
+  if (r != 0) {
+    cudaFreeAsync(ws, st);
+    return set_error(EVDR_ERR_NCCL, "ncclAllGather failed: %s", api->GetErrorString(r));
+  }
+  place_blocks_kernel<<<(unsigned)((blk * world + 255) / 256), 256, 0, st>>>(recv, world, B, np_total, cmax, out,
+                                                                             out_ld);
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(ws, st);
+  if (le != cudaSuccess)
+    return set_error(EVDR_ERR_CUDA, "launch of place_blocks_kernel failed: %s", cudaGetErrorString(le));
   return EVDR_OK;
 }
 

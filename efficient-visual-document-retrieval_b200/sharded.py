@@ -122,3 +122,51 @@ class ShardedSearch:
         dist.all_gather(gs, loc_s.contiguous(), group=self.group)
         dist.all_gather(gi, loc_i.contiguous(), group=self.group)
         return self._merge(torch.cat(gs, dim=1), torch.cat(gi, dim=1), k)
+
+
+class _GatherScoreRows(torch.autograd.Function):
+    """(B, n_local) score block of this rank's pages -> full (B, n_total) rows on every rank; the backward
+    is the local column slice of the incoming gradient (each rank owns its pages' parameters: no reduce)."""
+
+    @staticmethod
+    def forward(ctx, local, n_total, mode, group):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        start, end = partition_pages(n_total, world)[rank]
+        if local.shape[1] != end - start:
+            raise ValueError(f"rank {rank} owns pages [{start}, {end}) but the score block has {local.shape[1]} columns")
+        ctx.range = (start, end)
+        B = local.shape[0]
+        src = local.detach().to(torch.float32)
+        if mode == "nccl":
+            _lib.require_cuda(src, "local_scores")
+            if src.stride(1) != 1:
+                src = src.contiguous()
+            out = torch.empty((B, n_total), dtype=torch.float32, device=src.device)
+            lib = _lib.load()
+            _lib.check(lib.evdr_allgather_score_rows(_lib.handle(src.device), src.data_ptr(), src.stride(0), B, n_total,
+                                                     out.data_ptr(), out.stride(0), _lib.stream_ptr(src.device)),
+                       "evdr_allgather_score_rows")
+            return out
+        # torch.distributed on whatever backend the group has (gloo in the CPU tests): equal-size blocks
+        cmax = partition_pages(n_total, world)[0][1]
+        pad = torch.zeros((B, cmax), dtype=torch.float32, device=src.device)
+        pad[:, : end - start] = src
+        blocks = [torch.empty_like(pad) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(blocks, pad, group=group)
+        else:
+            blocks = [pad]
+        return torch.cat([blk[:, : e - s] for blk, (s, e) in zip(blocks, partition_pages(n_total, world))], dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        s, e = ctx.range
+        return g[:, s:e].contiguous(), None, None, None
+
+
+def gather_score_rows(local_scores: torch.Tensor, n_total: int, *, mode: str = "nccl", group=None) -> torch.Tensor:
+    """Training collective of SURVEY.md 8e: full (B, n_total) score rows on every rank from per-rank column
+    blocks (pages partitioned by `partition_pages`), differentiable -- the gradient of a rank's block is the
+    matching column slice.  mode="nccl": ncclAllGather inside libevdr.so; "torchdist": torch.distributed."""
+    return _GatherScoreRows.apply(local_scores, int(n_total), mode, group)

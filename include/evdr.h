@@ -260,6 +260,14 @@ EVDR_API int evdr_sharded_topk(evdr_handle* h, const float* local_scores_dev, in
                                int nq, int np_local, int k, int64_t id_offset,
                                float* top_scores_dev, int64_t* top_ids_dev, void* stream);
 
+/* Training collective: every rank scores the batch against ITS pages; the loss needs full
+ * (B, Np) rows on every rank.  Pages are partitioned contiguously, the first np_total % world ranks
+ * own one page more (rank r: np_total / world (+1) columns starting at r * (np_total / world) +
+ * min(r, np_total % world)).  One ncclAllGather of the zero-padded column blocks, placed by page offset.
+ * The backward of this step is the local column slice of d(loss)/d(scores): no collective. */
+EVDR_API int evdr_allgather_score_rows(evdr_handle* h, const float* local_scores_dev, int64_t ld, int B,
+                                       int np_total, float* out_dev, int64_t out_ld, void* stream);
+
 /* Peer-memory exchange (no NCCL on the data path): every rank owns an exchange region shared through
  * CUDA IPC; ONE kernel copies the local top-k of each query into all peers' regions with remote
  * stores over NVLink, releases per-query flags, acquires the peers' flags and merges the world * k

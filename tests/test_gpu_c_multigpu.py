@@ -50,6 +50,14 @@ def _worker(rank, world, port, ret):
         ok = ok and torch.equal(pi, ni) and torch.equal(ps, ns)
         ps, pi = peer.topk(local[:1], 3)
         ok = ok and torch.equal(pi, top_i[:1, :3])
+        # training collective: full (nq, n_pages) rows from the per-rank column blocks (unequal widths),
+        # gradient of the local block = the local column slice
+        loc = local.clone().requires_grad_(True)
+        rows = evdr.gather_score_rows(loc, n_pages)
+        ok = ok and torch.allclose(rows, full, rtol=0, atol=1e-5)
+        wgt = torch.randn(nq, n_pages, generator=torch.Generator().manual_seed(1)).to(dev)
+        (rows * wgt).sum().backward()
+        ok = ok and torch.equal(loc.grad, wgt[:, lo:hi])
         gathered = [None] * world
         dist.all_gather_object(gathered, top_i.cpu().tolist())
         ok = ok and all(g == gathered[0] for g in gathered)
@@ -96,3 +104,14 @@ def test_peer_exchange_single_rank(evdr, cuda):
         assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
     with pytest.raises(ValueError):
         evdr.ShardedSearch((0, 10), mode="peer").topk(torch.zeros(400, 10, device=cuda), 16)   # > region
+
+
+def test_gather_score_rows_single_rank(evdr, cuda):
+    s = torch.randn(6, 45, device=cuda)
+    wide = torch.zeros(6, 64, device=cuda)
+    wide[:, :45] = s
+    loc = wide[:, :45].requires_grad_(True)                   # strided rows
+    rows = evdr.gather_score_rows(loc, 45)
+    assert torch.equal(rows, s)
+    rows.sum().backward()
+    assert torch.equal(loc.grad, torch.ones_like(s))

@@ -78,3 +78,41 @@ def test_sharded_topk_world2_gloo(n_pages, k):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(0) and ret.get(1)
+
+
+def _gather_worker(rank, world, port, n_pages, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import evdr_b200 as evdr
+        g = torch.Generator().manual_seed(7)
+        full = torch.randn(4, n_pages, generator=g)              # identical on both ranks
+        w = torch.randn(4, n_pages, generator=g)
+        lo, hi = evdr.partition_pages(n_pages, world)[rank]
+        local = full[:, lo:hi].clone().requires_grad_(True)
+        rows = evdr.gather_score_rows(local, n_pages, mode="torchdist")
+        ok = torch.equal(rows, full)
+        (rows * w).sum().backward()                               # d/d(local) = the local column slice of w
+        ok = ok and torch.equal(local.grad, w[:, lo:hi])
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pages", [10, 7, 1001])
+def test_gather_score_rows_world2_gloo(n_pages):
+    """Training collective: full (B, Np) rows on every rank from per-rank column blocks of
+    unequal width; the backward is the local slice."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_pages, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(0) and ret.get(1)
