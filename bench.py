@@ -442,9 +442,12 @@ def host_corpus_e2e(evdr, torch, corpus, Qh, qmh, host_scores, dev, timed, steps
         host_scores.copy_(hc.score(Qd, qd), non_blocking=True)
 
     ms = timed(step, max(3, steps), 2)
+    # what the link itself does: the same pinned buffer copied to the device with nothing else running
+    ms_copy = timed(lambda: hc._stage[0].copy_(host[: hc.ppc], non_blocking=True), 5, 2)
+    link_gbs = hc.ppc * corpus.shape[1] * corpus.shape[2] * 2 / (ms_copy * 1e-3) / 1e9
     h2d = need + Qh.numel() * 4 + qmh.numel()
     return {"value": pairs_per_step / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": host_scores.numel() * 4, "h2d_gbs": h2d / (ms * 1e-3) / 1e9,
+            "d2h_bytes_per_step": host_scores.numel() * 4, "h2d_gbs": h2d / (ms * 1e-3) / 1e9, "h2d_copy_only_gbs": link_gbs,
             "pages_per_chunk": hc.ppc,
             "call": "HostCorpus(pinned bf16 corpus).score(Q, qmask): corpus, queries and masks start in pinned "
                     "host memory every step; scores are read back"}

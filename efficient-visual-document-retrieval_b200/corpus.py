@@ -269,12 +269,17 @@ class HostCorpus:
         full = torch.empty((rows, self.n_pages), dtype=torch.float32, device=dev) if (out is None or G > 1) else out
         main = torch.cuda.current_stream(dev)
         cs = self._copy_stream
-        n_chunks = (self.n_pages + self.ppc - 1) // self.ppc
+        # chunk sizes ramp up (ppc/16, ppc/8, ... ppc): only the FIRST copy is exposed, so it is kept small
+        bounds, c, step = [0], 0, max(1, self.ppc // 16)
+        while c < self.n_pages:
+            c = min(self.n_pages, c + step)
+            bounds.append(c)
+            step = min(self.ppc, step * 2)
         # the staging buffers may still be read by a previous call on this stream
         cs.wait_stream(main)
-        for i in range(n_chunks):
+        for i in range(len(bounds) - 1):
             b = i & 1
-            c0, c1 = i * self.ppc, min(self.n_pages, (i + 1) * self.ppc)
+            c0, c1 = bounds[i], bounds[i + 1]
             with torch.cuda.stream(cs):
                 if i >= 2:
                     cs.wait_event(self._consumed[b])       # the kernel of chunk i-2 is done with buffer b
