@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--no-extras", action="store_true", help="skip the single-query / 64-query side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="candidate exchange at N > 1: ncclAllGather + merge, or the one-kernel peer-memory exchange")
     ap.add_argument("--corpus-1m", action="store_true", help="also run the 1M-page top-10 QPS measurement at 2 GPUs")
     args = ap.parse_args()
@@ -247,7 +247,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         evdr.init_nccl_comm(dev)
         if args.exchange == "peer":
-            evdr.init_peer_exchange(dev, max_candidates=max(args.queries, 64) * TOPK)
+            # init_peer_exchange either succeeds on every rank or raises on every rank (CUDA IPC peer
+            # access unavailable somewhere): then all ranks use the NCCL exchange
+            try:
+                evdr.init_peer_exchange(dev, max_candidates=max(args.queries, 64) * TOPK)
+            except Exception as e:
+                print(f"[bench] peer exchange unavailable on rank {rank}: {e!r}; using NCCL", file=sys.stderr)
+                args.exchange = "nccl"
     n_gpus = world
     xmode = args.exchange if world > 1 else "nccl"
     peaks = load_peaks()
@@ -350,6 +356,12 @@ def main():
                                                             args.steps, pairs_per_step)
             except Exception as e:
                 extras["e2e_host_corpus"] = {"error": repr(e)}
+        # candidate exchange alone (local top-10 + exchange + merge of resident scores), both modes
+        if n_gpus > 1:
+            try:
+                extras["exchange_us"] = exchange_latency(evdr, torch, dev, rank, npg, timed, xmode)
+            except Exception as e:
+                extras["exchange_us"] = {"error": repr(e)}
         # BASELINE.json configs[3]: top-10 QPS on a 1 M-page corpus sharded over the box (needs the
         # memory of >= 4 GPUs at 100k pages already resident; 2 GPUs only with --corpus-1m)
         if n_gpus >= 4 or (n_gpus >= 2 and args.corpus_1m):
@@ -416,6 +428,18 @@ def corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed, xmode="nccl"):
             rec["tflops_per_gpu"] = tf
             rec["frac_of_bf16_burst_peak"] = tf / peaks["bf16_tflops"]
         out[f"q{nq}"] = rec
+    return out
+
+
+def exchange_latency(evdr, torch, dev, rank, npg, timed, xmode):
+    """us per ShardedSearch.topk call on resident (nq, npg) score blocks: ncclAllGather + unpack + merge vs
+    the one-kernel peer-memory exchange (only measured when the peer regions were set up)."""
+    out = {}
+    for nq in (1, 64):
+        s = torch.randn((nq, npg), device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
+        for mode in (["nccl", "peer"] if xmode == "peer" else ["nccl"]):
+            ss = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode=mode)
+            out[f"q{nq}_{mode}"] = timed(lambda: ss.topk(s, TOPK), 50, 5) * 1e3
     return out
 
 

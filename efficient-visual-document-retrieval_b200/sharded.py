@@ -57,24 +57,44 @@ def init_peer_exchange(device: torch.device, group=None, max_candidates: int = 6
     """Set up libevdr's peer-memory exchange for this rank: allocate the exchange region, gather every
     rank's CUDA IPC handle with torch.distributed (the plumbing) and open the peers' regions.  After this
     ShardedSearch(mode="peer") needs no NCCL call on the data path.  `max_candidates` bounds nq * k per
-    search (default: 64 queries x top-128, or 819 queries x top-10)."""
+    search (default: 64 queries x top-128, or 819 queries x top-10).
+
+    Collective and failure-consistent: every rank takes part in both exchanges even when its own step
+    failed, and either all ranks return or all raise (so callers can fall back to mode="nccl" together)."""
     lib = _lib.load()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     h = _lib.handle(device)
     if lib.evdr_peer_world(h) == world:
         return
+    on_dev = dist.get_backend(group) == "nccl"
+
+    def gather_bytes(payload: bytes):
+        mine = torch.tensor(list(payload), dtype=torch.uint8)
+        mine = mine.to(device) if on_dev else mine
+        allt = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine, group=group)
+        return [bytes(t.cpu().tolist()) for t in allt]
+
+    err = None
     buf = (C.c_ubyte * 64)()
-    _lib.check(lib.evdr_peer_region_init(h, rank, world, int(max_candidates), C.cast(buf, C.c_void_p)),
-               "evdr_peer_region_init")
-    mine = torch.tensor(list(buf), dtype=torch.uint8)
-    backend = dist.get_backend(group)
-    mine = mine.to(device) if backend == "nccl" else mine
-    allh = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allh, mine, group=group)
-    raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
-    blob = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
-    _lib.check(lib.evdr_peer_connect(h, C.cast(blob, C.c_void_p)), "evdr_peer_connect")
-    dist.barrier(group=group)      # nobody pushes into a region before its owner has opened everyone
+    try:
+        _lib.check(lib.evdr_peer_region_init(h, rank, world, int(max_candidates), C.cast(buf, C.c_void_p)),
+                   "evdr_peer_region_init")
+    except Exception as e:          # still take part in the exchange below
+        err = e
+    got = gather_bytes(bytes(buf) + (b"\x01" if err is None else b"\x00"))
+    if err is None and all(g[64] == 1 for g in got):
+        raw = b"".join(g[:64] for g in got)
+        blob = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        try:
+            _lib.check(lib.evdr_peer_connect(h, C.cast(blob, C.c_void_p)), "evdr_peer_connect")
+        except Exception as e:
+            err = e
+    elif err is None:
+        err = _lib.EvdrError("a peer rank could not allocate its exchange region")
+    ok = gather_bytes(b"\x01" if err is None else b"\x00")   # also the barrier: nobody pushes into a region
+    if not all(o[0] == 1 for o in ok):                          # before its owner has opened everyone
+        raise _lib.EvdrError(f"peer-memory exchange unavailable: {err or 'a peer rank failed to connect'}")
 
 
 class ShardedSearch:
