@@ -13,7 +13,8 @@ package ``evdr_b200`` at the repository root.
 from . import _lib
 from . import corpus, losses, mining, normalize, retrieval, sharded, synth, topk
 from .corpus import HostCorpus, PackedPages, pack_queries
-from .losses import (liscore_losses, listwise_distillation_loss, pairwise_distillation_loss, rank_gap,
+from .losses import (infonce_distillation_loss, infonce_supervised_loss, lambda_loss, liscore_losses,
+                     listwise_distillation_loss, pairwise_distillation_loss, rank_gap, ranknce_loss,
                      score_preserving_loss)
 from .mining import hard_token_argmax, hard_tokens
 from .normalize import l2_normalize, l2_normalize_masked

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "evdr_rank_gap": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "evdr_liscore_loss": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _i, C.c_float, _vp, _vp, _vp, _vp, _vp], _i),
     "evdr_pairwise_loss": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "evdr_lambda_loss": ([_vp, _vp, _i64, _vp, _i64, _i, _i, C.c_float, C.c_float, _vp, _vp, _vp, _vp], _i),
+    "evdr_ranknce_loss": ([_vp, _vp, _i64, _vp, _i64, _i, _i, C.c_float, C.c_float, _vp, _vp, _vp, _vp], _i),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -203,6 +203,147 @@ pairwise_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __r
   }
 }
 
+__device__ __forceinline__ float softplusf_(float x) {          // log(1 + exp(x)), stable
+  return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+
+// criterion.py:148-189 (lambda_loss).  With p(i) = teacher rank of page i (0 = best) the reference's
+// sort + upper-triangle mask is "every pair with p(i) < p(j)":
+//   w_ij = 10 * |sig(t_i) - sig(t_j)| * |1/log2(p(i)+2) - 1/log2(p(j)+2)|
+//   loss = sum_{b, p(i)<p(j)} w_ij * softplus(-alpha (s_i - s_j)) / (N(N-1)/2 + eps)        (summed over b)
+// grid (ceil(n / LOSS_THREADS), B): thread = page i, loop over all j.
+__global__ void __launch_bounds__(LOSS_THREADS)
+lambda_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __restrict__ sc_t,
+              long long ld_t, int B, int n, float alpha, float eps, float* __restrict__ grad,
+              float* __restrict__ part, float* __restrict__ loss, int* __restrict__ done) {
+  extern __shared__ float sm[];
+  float* t = sm;                                   // sigmoid(t) after the rank pass
+  float* s = sm + n;
+  float* disc = sm + 2 * n;                        // 1 / log2(rank + 2) of page i
+  __shared__ float red[32];
+  __shared__ int last;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    t[i] = sc_t[(size_t)b * ld_t + i];
+    s[i] = sc_s[(size_t)b * ld_s + i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) disc[i] = 1.f / log2f((float)desc_rank(t, n, i) + 2.f);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) t[i] = sigmoidf_(t[i]);
+  __syncthreads();
+  const float denom = 0.5f * (float)n * (float)(n - 1) + eps;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f, gacc = 0.f;
+  if (i < n) {
+    const float si = s[i], ri = t[i], di = disc[i];
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      const float dj = disc[j];
+      const float w = 10.f * fabsf(ri - t[j]) * fabsf(di - dj);
+      // larger discount = better teacher rank (ranks are a permutation: no equal discounts)
+      if (di > dj) {                               // i ranked above j: term softplus(-alpha (s_i - s_j))
+        const float x = alpha * (si - s[j]);
+        acc += w * softplusf_(-x);
+        gacc -= w * alpha * sigmoidf_(-x);
+      } else {                                     // j ranked above i: term softplus(-alpha (s_j - s_i))
+        const float x = alpha * (s[j] - si);
+        gacc += w * alpha * sigmoidf_(-x);
+      }
+    }
+    grad[(size_t)b * n + i] = gacc / denom;
+  }
+  acc = block_reduce(acc, red, false);
+  const int nblk = gridDim.x * gridDim.y;
+  if (threadIdx.x == 0) {
+    part[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+    __threadfence();
+    last = (atomicAdd(done, 1) == nblk - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* pp = part;
+    double tot = 0.0;
+    for (int r = 0; r < nblk; ++r) tot += (double)pp[r];
+    loss[0] = (float)(tot / (double)denom);
+  }
+}
+
+// criterion.py:192-226 (ranknce_loss).  o(0), o(1), ... = pages in descending teacher order:
+//   infonce = mean_b ( logsumexp_i(s_i / T) - s_o(0) / T )
+//   ranking = mean_{b, k < N-1} sig(t_o(k) - t_o(k+1)) * softplus(-(s_o(k) - s_o(k+1)))
+//   loss = infonce + lambda * ranking;   row_loss[b] = {infonce_b, sum_k ranking_bk}
+// one CTA per query row.
+__global__ void __launch_bounds__(LOSS_THREADS)
+ranknce_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __restrict__ sc_t,
+               long long ld_t, int B, int n, float T, float lambda_w, float* __restrict__ grad,
+               float* __restrict__ row_loss, float* __restrict__ loss, int* __restrict__ done) {
+  extern __shared__ float sm[];
+  float* t = sm;
+  float* s = sm + n;
+  int* order = reinterpret_cast<int*>(sm + 2 * n);     // order[p] = page at teacher rank p
+  float* g = sm + 3 * n;                                // gradient of the ranking term, per page
+  __shared__ float red[32];
+  __shared__ int last;
+  const int b = blockIdx.x;
+  float ms = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    t[i] = sc_t[(size_t)b * ld_t + i];
+    const float sv = sc_s[(size_t)b * ld_s + i];
+    s[i] = sv;
+    g[i] = 0.f;
+    ms = fmaxf(ms, sv);
+  }
+  ms = block_reduce(ms, red, true);                     // (syncs: t, s, g are visible)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) order[desc_rank(t, n, i)] = i;
+  const float invT = 1.f / T;
+  float zs = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) zs += expf((s[i] - ms) * invT);
+  zs = block_reduce(zs, red, false);                    // (syncs: order is visible)
+  // adjacent pairs in teacher order; pair k touches pages o(k) and o(k+1): thread k owns pair k and adds
+  // to g in two passes (even k, then odd k) so that no two threads touch the same page at once
+  float rk = 0.f;
+  const float pair_scale = (n > 1) ? lambda_w / ((float)B * (float)(n - 1)) : 0.f;
+  for (int par = 0; par < 2; ++par) {
+    for (int k = 2 * threadIdx.x + par; k + 1 < n; k += 2 * blockDim.x) {
+      const int a = order[k], c = order[k + 1];
+      const float w = sigmoidf_(t[a] - t[c]);
+      const float x = s[a] - s[c];
+      rk += w * softplusf_(-x);
+      const float d = -w * sigmoidf_(-x) * pair_scale;  // d/ds_a ; d/ds_c = -d
+      g[a] += d;
+      g[c] -= d;
+    }
+    __syncthreads();
+  }
+  rk = block_reduce(rk, red, false);
+  const int top = order[0];
+  const float ce_scale = invT / (float)B;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float ps = expf((s[i] - ms) * invT) / zs;
+    grad[(size_t)b * n + i] = ce_scale * (ps - (i == top ? 1.f : 0.f)) + g[i];
+  }
+  if (threadIdx.x == 0) {
+    row_loss[2 * b] = (ms * invT + logf(zs)) - s[top] * invT;
+    row_loss[2 * b + 1] = rk;
+    __threadfence();
+    last = (atomicAdd(done, 1) == B - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* rl = row_loss;
+    float l0 = 0.f, l1 = 0.f;
+    for (int r = 0; r < B; ++r) { l0 += rl[2 * r]; l1 += rl[2 * r + 1]; }
+    l0 /= (float)B;
+    l1 = (n > 1) ? l1 / ((float)B * (float)(n - 1)) : 0.f;
+    loss[0] = l0 + lambda_w * l1;
+    loss[1] = l0;
+    loss[2] = l1;
+  }
+}
+
 static int next_counter(evdr_handle* h, cudaStream_t st, int** out) {
   int* c = h->sched_ring + (h->sched_next++ % EVDR_SCHED_RING);
   EVDR_CUDA(cudaMemsetAsync(c, 0, sizeof(int), st));
@@ -280,5 +421,46 @@ extern "C" int evdr_pairwise_loss(evdr_handle* h, const float* sc_s, int64_t ld_
   dim3 grid((n + LOSS_THREADS - 1) / LOSS_THREADS, B);
   pairwise_kernel<<<grid, LOSS_THREADS, smem, st>>>(sc_s, ld_s, sc_t, ld_t, B, n, grad, part_ws, loss1, done);
   EVDR_LAUNCH_CHECK("pairwise_kernel");
+  return EVDR_OK;
+}
+
+extern "C" int evdr_lambda_loss(evdr_handle* h, const float* sc_s, int64_t ld_s, const float* sc_t, int64_t ld_t,
+                                int B, int n, float alpha, float eps, float* grad, float* part_ws, float* loss1,
+                                void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(sc_s && sc_t && grad && part_ws && loss1, "evdr_lambda_loss: null pointer");
+  EVDR_CHECK_ARG(B >= 1 && B <= 65535 && n >= 1 && ld_t >= n && ld_s >= n, "evdr_lambda_loss: bad shape B=%d n=%d", B, n);
+  const size_t smem = sizeof(float) * 3 * (size_t)n;
+  if (smem > h->smem_optin)
+    return set_error(EVDR_ERR_UNSUPPORTED, "evdr_lambda_loss: n=%d rows do not fit shared memory", n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* done = nullptr;
+  int rc = next_counter(h, st, &done);
+  if (rc != EVDR_OK) return rc;
+  EVDR_CUDA(cudaFuncSetAttribute(lambda_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((n + LOSS_THREADS - 1) / LOSS_THREADS, B);
+  lambda_kernel<<<grid, LOSS_THREADS, smem, st>>>(sc_s, ld_s, sc_t, ld_t, B, n, alpha, eps, grad, part_ws, loss1, done);
+  EVDR_LAUNCH_CHECK("lambda_kernel");
+  return EVDR_OK;
+}
+
+extern "C" int evdr_ranknce_loss(evdr_handle* h, const float* sc_s, int64_t ld_s, const float* sc_t, int64_t ld_t,
+                                 int B, int n, float temperature, float lambda_weight, float* grad,
+                                 float* row_loss_ws, float* loss3, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(sc_s && sc_t && grad && row_loss_ws && loss3, "evdr_ranknce_loss: null pointer");
+  EVDR_CHECK_ARG(B >= 1 && n >= 1 && ld_t >= n && ld_s >= n, "evdr_ranknce_loss: bad shape B=%d n=%d", B, n);
+  EVDR_CHECK_ARG(temperature > 0.f, "evdr_ranknce_loss: temperature must be positive");
+  const size_t smem = sizeof(float) * 4 * (size_t)n;
+  if (smem > h->smem_optin)
+    return set_error(EVDR_ERR_UNSUPPORTED, "evdr_ranknce_loss: n=%d rows do not fit shared memory", n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* done = nullptr;
+  int rc = next_counter(h, st, &done);
+  if (rc != EVDR_OK) return rc;
+  EVDR_CUDA(cudaFuncSetAttribute(ranknce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ranknce_kernel<<<B, LOSS_THREADS, smem, st>>>(sc_s, ld_s, sc_t, ld_t, B, n, temperature, lambda_weight, grad,
+                                                row_loss_ws, loss3, done);
+  EVDR_LAUNCH_CHECK("ranknce_kernel");
   return EVDR_OK;
 }

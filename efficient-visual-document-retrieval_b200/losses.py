@@ -10,9 +10,12 @@ and the gradient w.r.t. the student scores -- the ``g`` that evdr_maxsim_bwd con
   without the three (B, N, N) intermediates
 * ``rank_gap(sc_t, sc_s, k, aux_docs)``   <- mainv3_iter_liscore_QA_hardtoken.py:368-385
 
+* ``lambda_loss(score_s, score_t, alpha, eps)``                             <- criterion.py:148-189
+* ``ranknce_loss(score_s, score_t, temperature, lambda_weight)``            <- criterion.py:192-226
+* ``infonce_supervised_loss`` / ``infonce_distillation_loss``               <- criterion.py:43-68 (one
+  library cross-entropy call each; listed so that ``dropin/criterion.py`` covers the whole module)
+
 The teacher scores are treated as constants exactly like the reference's ``score_t.detach()``.
-The remaining criterion.py losses (InfoNCE variants, lambda, RankNCE) are single torch library calls
-on a (32, N) matrix and stay with the caller.
 """
 from __future__ import annotations
 
@@ -107,6 +110,65 @@ class _PairwiseFn(torch.autograd.Function):
 def pairwise_distillation_loss(score_s: torch.Tensor, score_t: torch.Tensor) -> torch.Tensor:
     """criterion.py:89-110: mean over (b, i, j) of BCE-with-logits(s_i - s_j, sigmoid(t_i - t_j))."""
     return _PairwiseFn.apply(score_s, score_t)
+
+
+class _GradLossFn(torch.autograd.Function):
+    """Shared shape of the single-output losses: the kernel returns the loss and d(loss)/d(score_s)."""
+
+    @staticmethod
+    def forward(ctx, score_s, score_t, which, p0, p1):
+        s, t = _rows(score_s, "score_s"), _rows(score_t, "score_t")
+        if s.shape != t.shape:
+            raise ValueError(f"score_s {tuple(s.shape)} and score_t {tuple(t.shape)} differ")
+        B, n = s.shape
+        dev = s.device
+        grad = torch.empty((B, n), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        h, st = _lib.handle(dev), _lib.stream_ptr(dev)
+        if which == "lambda":
+            ws = torch.empty(B * ((n + 255) // 256), dtype=torch.float32, device=dev)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.check(lib.evdr_lambda_loss(h, s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0), B, n, float(p0),
+                                            float(p1), grad.data_ptr(), ws.data_ptr(), loss.data_ptr(), st),
+                       "evdr_lambda_loss")
+        else:
+            ws = torch.empty(2 * B, dtype=torch.float32, device=dev)
+            loss = torch.empty(3, dtype=torch.float32, device=dev)
+            _lib.check(lib.evdr_ranknce_loss(h, s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0), B, n, float(p0),
+                                             float(p1), grad.data_ptr(), ws.data_ptr(), loss.data_ptr(), st),
+                       "evdr_ranknce_loss")
+        ctx.save_for_backward(grad)
+        ctx.in_dtype = score_s.dtype
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (g * grad).to(ctx.in_dtype), None, None, None, None
+
+
+def lambda_loss(score_s: torch.Tensor, score_t: torch.Tensor, alpha: float = 1.0, eps: float = 1e-6) -> torch.Tensor:
+    """criterion.py:148-189: teacher-ranked pairs weighted by |delta gain| * |delta discount| * 10 on
+    softplus(-alpha * (s_i - s_j)); no (B, N, N) tensors."""
+    return _GradLossFn.apply(score_s, score_t, "lambda", alpha, eps)
+
+
+def ranknce_loss(score_s: torch.Tensor, score_t: torch.Tensor, temperature: float = 1.0,
+                 lambda_weight: float = 1.0) -> torch.Tensor:
+    """criterion.py:192-226: InfoNCE against the teacher's best page + lambda_weight * adjacent-pair ranking
+    regulariser in teacher order; no sort, no gathers."""
+    return _GradLossFn.apply(score_s, score_t, "ranknce", temperature, lambda_weight)
+
+
+def infonce_supervised_loss(score_s: torch.Tensor, labels: torch.Tensor, temperature: float = 0.07) -> torch.Tensor:
+    """criterion.py:43-54: a single library call (cross entropy) on the (B, N) scores."""
+    return torch.nn.functional.cross_entropy(score_s / temperature, labels)
+
+
+def infonce_distillation_loss(score_s: torch.Tensor, score_t: torch.Tensor, temperature: float = 0.07) -> torch.Tensor:
+    """criterion.py:57-68: cross entropy against the teacher's arg-max page."""
+    targets = torch.argmax(score_t.detach(), dim=1)
+    return torch.nn.functional.cross_entropy(score_s / temperature, targets)
 
 
 class RankGap(NamedTuple):

@@ -330,6 +330,20 @@ EVDR_API int evdr_liscore_loss(evdr_handle* h, const float* sc_s_dev, int64_t ld
 EVDR_API int evdr_pairwise_loss(evdr_handle* h, const float* sc_s_dev, int64_t ld_s, const float* sc_t_dev,
                                 int64_t ld_t, int B, int n, float* grad_dev, float* part_ws_dev,
                                 float* loss1_dev, void* stream);
+/* evdr_lambda_loss -- criterion.py:148-189 (lambda_loss): pairs ordered by the TEACHER ranking, weight
+ *   10 * |sigmoid(t_i) - sigmoid(t_j)| * |1/log2(rank_i + 2) - 1/log2(rank_j + 2)|, term
+ *   softplus(-alpha * (s_i - s_j)) for the better-ranked i, summed over the batch and divided by
+ *   N(N-1)/2 + eps; loss1[0] and d/d(sc_s).  part_ws: B * ceil(n / 256) floats.
+ * evdr_ranknce_loss -- criterion.py:192-226 (ranknce_loss): InfoNCE with the teacher's best page as the
+ *   positive (cross entropy of sc_s / T) + lambda_weight * mean over adjacent pairs of the teacher order of
+ *   sigmoid(t_k - t_k+1) * softplus(-(s_k - s_k+1)); loss3 = {total, infonce, ranking}, d/d(sc_s) of the
+ *   total.  row_loss_ws: 2*B floats.  (n == 1: the ranking term is 0 where the reference's empty mean is NaN.) */
+EVDR_API int evdr_lambda_loss(evdr_handle* h, const float* sc_s_dev, int64_t ld_s, const float* sc_t_dev,
+                              int64_t ld_t, int B, int n, float alpha, float eps, float* grad_dev,
+                              float* part_ws_dev, float* loss1_dev, void* stream);
+EVDR_API int evdr_ranknce_loss(evdr_handle* h, const float* sc_s_dev, int64_t ld_s, const float* sc_t_dev,
+                               int64_t ld_t, int B, int n, float temperature, float lambda_weight,
+                               float* grad_dev, float* row_loss_ws_dev, float* loss3_dev, void* stream);
 
 #ifdef __cplusplus
 }

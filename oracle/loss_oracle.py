@@ -90,3 +90,59 @@ def rank_gap(sc_t, sc_s, k: int = 10, aux_docs: int = 0):
     pos = np.argsort(-gap_topk, axis=1, kind="stable")[:, :a]       # :381
     aux = np.take_along_axis(topk_idx, pos, axis=1)                 # :382
     return {"gap": gap, "G": G, "rank_t": rank_t, "rank_s": rank_s, "topk_idx": topk_idx, "aux_doc_idx": aux}
+
+
+def lambda_loss(score_s, score_t, alpha: float = 1.0, eps: float = 1e-6):
+    """criterion.py:148-189.  Returns (loss, dloss/dscore_s)."""
+    s = np.asarray(score_s, dtype=np.float64)
+    t = np.asarray(score_t, dtype=np.float64)
+    B, n = s.shape
+    _, order = _desc_ranks(t)                                       # :162
+    rows = np.arange(B)[:, None]
+    ss, ts = s[rows, order], t[rows, order]                         # :163
+    # The gain and discount factors are kept in float32 like the reference: MaxSim scores are ~10-30, where
+    # sigmoid(t) = 1 - O(1e-6) and |sig(t_i) - sig(t_j)| is a small multiple of the fp32 spacing 6e-8 -- the
+    # reference's value IS that quantised number, an exact sigmoid would differ from it by percents.
+    f32 = np.float32
+    disc = (f32(1.0) / np.log2(np.arange(1, n + 1, dtype=f32) + f32(1.0))).astype(f32)          # :167-168
+    ddiff = np.abs(disc[None, :, None] - disc[None, None, :]).astype(np.float64)                # :171
+    rel = (f32(1.0) / (f32(1.0) + np.exp(-ts.astype(f32)))).astype(f32)                         # :174
+    w = np.abs(rel[:, :, None] - rel[:, None, :]).astype(np.float64) * ddiff * 10.0             # :175-178
+    x = alpha * (ss[:, :, None] - ss[:, None, :])                   # :181
+    sp = np.maximum(-x, 0.0) + np.log1p(np.exp(-np.abs(x)))         # -logsigmoid(x), :182
+    mask = np.triu(np.ones((n, n)), k=1)                            # :186
+    denom = mask.sum() + eps
+    loss = (w * sp * mask).sum() / denom                            # :187
+    dsp = -alpha / (1.0 + np.exp(x))                                # d softplus(-x) / d s_i
+    gm = w * dsp * mask
+    gs = (gm.sum(axis=2) - gm.sum(axis=1)) / denom                  # in sorted order
+    grad = np.empty_like(gs)
+    grad[rows, order] = gs
+    return loss, grad
+
+
+def ranknce_loss(score_s, score_t, temperature: float = 1.0, lambda_weight: float = 1.0):
+    """criterion.py:192-226.  Returns (loss, dloss/dscore_s)."""
+    s = np.asarray(score_s, dtype=np.float64)
+    t = np.asarray(score_t, dtype=np.float64)
+    B, n = s.shape
+    _, order = _desc_ranks(t)                                       # :206
+    rows = np.arange(B)[:, None]
+    ss, ts = s[rows, order], t[rows, order]                         # :207
+    p = _softmax(ss / temperature)
+    infonce = -np.log(p[:, 0]).mean()                               # :210-211 (label 0)
+    ds, dt = ss[:, :-1] - ss[:, 1:], ts[:, :-1] - ts[:, 1:]         # :214-215
+    w = 1.0 / (1.0 + np.exp(-dt))                                   # :221
+    sp = np.maximum(-ds, 0.0) + np.log1p(np.exp(-np.abs(ds)))       # softplus(-ds)
+    ranking = (w * sp).mean() if n > 1 else 0.0                     # :222
+    loss = infonce + lambda_weight * ranking                        # :224
+    gs = p.copy()
+    gs[:, 0] -= 1.0
+    gs /= (B * temperature)
+    if n > 1:
+        d = -w / (1.0 + np.exp(ds)) * (lambda_weight / (B * (n - 1)))
+        gs[:, :-1] += d
+        gs[:, 1:] -= d
+    grad = np.empty_like(gs)
+    grad[rows, order] = gs
+    return loss, grad

@@ -63,7 +63,10 @@ def main():
         out[f"{name}/t"] = t.numpy()
         for fn, key, kw in ((crit.listwise_distillation_loss, "listwise", {"k": k, "temperature": T}),
                             (crit.score_preserving_loss, "mse", {}),
-                            (crit.pairwise_distillation_loss, "pairwise", {})):
+                            (crit.pairwise_distillation_loss, "pairwise", {}),
+                            (crit.lambda_loss, "lambda", {"alpha": 1.0 if T == 1.0 else 0.5}),
+                            (crit.ranknce_loss, "ranknce", {"temperature": T, "lambda_weight": 0.7}),
+                            (crit.infonce_distillation_loss, "infonce_distill", {"temperature": 0.07})):
             sg = s.clone().requires_grad_(True)
             loss = fn(sg, t, **kw)
             loss.backward()

@@ -163,10 +163,15 @@ def test_loss_oracle_matches_reference(name):
     s, t = z[f"{name}/s"], z[f"{name}/t"]
     for key, (loss, grad) in {"listwise": lo.listwise_distillation_loss(s, t, k, T),
                               "mse": lo.score_preserving_loss(s, t),
-                              "pairwise": lo.pairwise_distillation_loss(s, t)}.items():
-        np.testing.assert_allclose(loss, z[f"{name}/{key}_loss"], rtol=2e-5, err_msg=key)
+                              "pairwise": lo.pairwise_distillation_loss(s, t),
+                              "lambda": lo.lambda_loss(s, t, alpha=1.0 if T == 1.0 else 0.5),
+                              "ranknce": lo.ranknce_loss(s, t, temperature=T, lambda_weight=0.7)}.items():
+        # lambda_loss: the oracle keeps the gain / discount factors in float32 like the reference (their
+        # differences are small multiples of the fp32 spacing); what remains is summation order
+        lr, gr, ga = (2e-5, 1e-3, 2e-5) if key == "lambda" else (2e-5, 2e-4, 2e-6)
+        np.testing.assert_allclose(loss, z[f"{name}/{key}_loss"], rtol=lr, err_msg=key)
         ref_g = z[f"{name}/{key}_grad"]
-        np.testing.assert_allclose(grad, ref_g, rtol=2e-4, atol=2e-6 * np.abs(ref_g).max(), err_msg=key)
+        np.testing.assert_allclose(grad, ref_g, rtol=gr, atol=ga * np.abs(ref_g).max(), err_msg=key)
     rg = lo.rank_gap(t, s, k, aux)
     for key, ref_key in (("rank_t", "rank_t"), ("rank_s", "rank_s"), ("gap", "gap"), ("G", "G"),
                          ("topk_idx", "topk_idx")):
