@@ -211,6 +211,147 @@ topk_select_kernel(const float* __restrict__ scores, long long ld, int n,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k <= 32: the per-warp list lives in REGISTERS (lane j = j-th best so far), an insertion is one ballot
+// and three shuffle-ups instead of a shared-memory shift, four independent 32-column loads are in flight
+// per warp, and the threshold is bootstrapped from the lane maxima of the first 128 columns (their k-th
+// largest is a lower bound of the final k-th value), which removes the insertion storm of a cold list --
+// the whole cost when a warp only sees a few hundred columns (single-query search).
+// Same sources, outputs and ordering as topk_select_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_kth_largest(float v, int k, int lane) {
+  // bitonic sort of one value per lane, descending; returns the value at position k - 1
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, stride);
+      const bool desc = (lane & size) == 0;              // direction of this lane's block
+      const bool lower = (lane & stride) == 0;           // lower index of the compared pair
+      const bool keep_max = (desc == lower);
+      v = keep_max ? fmaxf(v, o) : fminf(v, o);
+    }
+  }
+  return __shfl_sync(0xffffffffu, v, k - 1);
+}
+
+__global__ void __launch_bounds__(TOPK_WARPS * 32)
+topk_small_kernel(const float* __restrict__ scores, long long ld, int n,
+                  const int32_t* __restrict__ tie_rank, long long id_offset,
+                  const long long* __restrict__ cand_ids, const long long* __restrict__ cand_tie,
+                  int k, float* __restrict__ out_s, long long* __restrict__ out_tie,
+                  long long* __restrict__ out_id, const MetricArgs ma) {
+  __shared__ float ws[TOPK_WARPS * 32];
+  __shared__ long long wt[TOPK_WARPS * 32];
+  __shared__ long long wi[TOPK_WARPS * 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.y;
+  const int nsplit = gridDim.x;
+  const int seg = (n + nsplit - 1) / nsplit;
+  const int beg = blockIdx.x * seg;
+  const int end = min(n, beg + seg);
+  const float* row = scores + (size_t)q * ld;
+  const long long* idrow = cand_ids ? cand_ids + (size_t)q * ld : nullptr;
+  const long long* tierow = cand_tie ? cand_tie + (size_t)q * ld : nullptr;
+  constexpr long long TIE_MAX = 0x7fffffffffffffffLL;
+
+  // this warp's contiguous slice of the CTA's range (coalesced 128-byte rows per load)
+  const int wseg = ((end - beg + TOPK_WARPS - 1) / TOPK_WARPS + 31) & ~31;
+  const int wbeg = min(end, beg + warp * wseg);
+  const int wend = min(end, wbeg + wseg);
+
+  float my_s = -INFINITY;                    // list entry `lane`
+  long long my_t = TIE_MAX, my_i = -1;
+  // bootstrap: k-th largest of the lane maxima over the first 128 columns of the slice
+  float thr_s;
+  long long thr_t = TIE_MAX;
+  {
+    float m = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = wbeg + u * 32 + lane;
+      if (i < wend && (!idrow || idrow[i] >= 0)) m = fmaxf(m, row[i]);
+    }
+    thr_s = warp_kth_largest(m, k, lane);
+  }
+  int filled = 0;                            // insertions so far (the list's k-th entry is real once >= k)
+  for (int base = wbeg; base < wend; base += 128) {
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 32 + lane;
+      s[u] = (i < wend) ? row[i] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 32 + lane;
+      long long t = TIE_MAX, id = -1;
+      bool ok = (i < wend) && (s[u] >= thr_s);          // cheap pre-test before touching tie / id arrays
+      if (ok) {
+        if (idrow) {
+          id = idrow[i];
+          t = tierow ? tierow[i] : id;
+          ok = id >= 0;
+        } else {
+          id = (long long)i + id_offset;
+          t = tie_rank ? (long long)tie_rank[i] : (long long)i;
+        }
+        ok = ok && better(s[u], t, thr_s, thr_t);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, ok);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float cs = __shfl_sync(0xffffffffu, s[u], src);
+        const long long ct = __shfl_sync(0xffffffffu, t, src);
+        const long long cid = __shfl_sync(0xffffffffu, id, src);
+        if (!better(cs, ct, thr_s, thr_t)) continue;    // the threshold may have moved
+        const int pos = __popc(__ballot_sync(0xffffffffu, better(my_s, my_t, cs, ct)));
+        const float us = __shfl_up_sync(0xffffffffu, my_s, 1);
+        const long long ut = __shfl_up_sync(0xffffffffu, my_t, 1);
+        const long long ui = __shfl_up_sync(0xffffffffu, my_i, 1);
+        if (lane == pos) { my_s = cs; my_t = ct; my_i = cid; }
+        else if (lane > pos) { my_s = us; my_t = ut; my_i = ui; }
+        if (++filled >= k) {                             // k real entries: the list's k-th is the bar
+          const float ls = __shfl_sync(0xffffffffu, my_s, k - 1);
+          const long long lt = __shfl_sync(0xffffffffu, my_t, k - 1);
+          if (better(ls, lt, thr_s, thr_t)) { thr_s = ls; thr_t = lt; }
+        }
+      }
+    }
+  }
+  ws[warp * 32 + lane] = my_s;
+  wt[warp * 32 + lane] = my_t;
+  wi[warp * 32 + lane] = my_i;
+  __syncthreads();
+  // block merge: rank every entry of the 8 lists (first k of each) among all of them
+  const int total = TOPK_WARPS * k;
+  float* os = out_s + ((size_t)q * nsplit + blockIdx.x) * k;
+  long long* ot = out_tie ? out_tie + ((size_t)q * nsplit + blockIdx.x) * k : nullptr;
+  long long* oi = out_id + ((size_t)q * nsplit + blockIdx.x) * k;
+  for (int e = tid; e < total; e += blockDim.x) {
+    const int w = e / k, j = e % k;
+    const float es = ws[w * 32 + j];
+    const long long et = wt[w * 32 + j];
+    int rank = 0;
+    for (int f = 0; f < total; ++f) {
+      const int fw = f / k, fj = f % k;
+      const float fs = ws[fw * 32 + fj];
+      const long long ft = wt[fw * 32 + fj];
+      if (better(fs, ft, es, et) || (fs == es && ft == et && f < e)) ++rank;
+    }
+    if (rank < k) {
+      os[rank] = es;
+      if (ot) ot[rank] = et;
+      oi[rank] = wi[w * 32 + j];
+    }
+  }
+  if (ma.out != nullptr) {
+    __syncthreads();
+    if (tid == 0) query_metrics(oi, k, q, gridDim.y, ma);
+  }
+}
+
 __global__ void __launch_bounds__(128)
 metrics_kernel(const long long* __restrict__ top_ids, int kmax, int nq, const MetricArgs ma) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,9 +383,14 @@ static int run_topk(evdr_handle* h, const float* scores, long long ld, int nq, i
   const size_t smem = topk_smem();
   EVDR_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nsplit = pick_nsplit(h, nq, n);
+  const bool small = k <= 32;                 // register-list kernel
   if (nsplit == 1) {
-    topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
-        scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, top_s, nullptr, top_id, fin);
+    if (small)
+      topk_small_kernel<<<dim3(1, nq), TOPK_WARPS * 32, 0, st>>>(
+          scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, top_s, nullptr, top_id, fin);
+    else
+      topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
+          scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, top_s, nullptr, top_id, fin);
     EVDR_LAUNCH_CHECK("topk_select_kernel");
     return EVDR_OK;
   }
@@ -254,12 +400,21 @@ static int run_topk(evdr_handle* h, const float* scores, long long ld, int nq, i
   long long* p_tie = reinterpret_cast<long long*>(ws);
   long long* p_id = p_tie + per;
   float* p_s = reinterpret_cast<float*>(p_id + per);
-  topk_select_kernel<<<dim3(nsplit, nq), TOPK_WARPS * 32, smem, st>>>(
-      scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, p_s, p_tie, p_id, none);
-  EVDR_LAUNCH_CHECK("topk_select_kernel(stage1)");
-  topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
-      p_s, (long long)nsplit * k, nsplit * k, nullptr, 0, p_id, p_tie, k, top_s, nullptr, top_id, fin);
-  EVDR_LAUNCH_CHECK("topk_select_kernel(stage2)");
+  if (small) {
+    topk_small_kernel<<<dim3(nsplit, nq), TOPK_WARPS * 32, 0, st>>>(
+        scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, p_s, p_tie, p_id, none);
+    EVDR_LAUNCH_CHECK("topk_small_kernel(stage1)");
+    topk_small_kernel<<<dim3(1, nq), TOPK_WARPS * 32, 0, st>>>(
+        p_s, (long long)nsplit * k, nsplit * k, nullptr, 0, p_id, p_tie, k, top_s, nullptr, top_id, fin);
+    EVDR_LAUNCH_CHECK("topk_small_kernel(stage2)");
+  } else {
+    topk_select_kernel<<<dim3(nsplit, nq), TOPK_WARPS * 32, smem, st>>>(
+        scores, ld, n, tie_rank, id_offset, cand_ids, nullptr, k, p_s, p_tie, p_id, none);
+    EVDR_LAUNCH_CHECK("topk_select_kernel(stage1)");
+    topk_select_kernel<<<dim3(1, nq), TOPK_WARPS * 32, smem, st>>>(
+        p_s, (long long)nsplit * k, nsplit * k, nullptr, 0, p_id, p_tie, k, top_s, nullptr, top_id, fin);
+    EVDR_LAUNCH_CHECK("topk_select_kernel(stage2)");
+  }
   EVDR_CUDA(cudaFreeAsync(ws, st));
   return EVDR_OK;
 }

@@ -179,7 +179,9 @@ def _oracle_topk(scores, k, tie=None):
     return vals, ids
 
 
-@pytest.mark.parametrize("nq,n,k", [(7, 500, 10), (3, 70, 100), (1, 200000, 10), (64, 3000, 128), (2, 5, 5)])
+@pytest.mark.parametrize("nq,n,k", [(7, 500, 10), (3, 70, 100), (1, 200000, 10), (64, 3000, 128), (2, 5, 5),
+                                    (5, 1000, 1), (4, 4097, 32), (3, 31, 32), (2, 129, 17), (1, 125000, 10),
+                                    (70, 100000, 10), (300, 1234, 33)])
 def test_topk_matches_sort(evdr, cuda, nq, n, k):
     g = torch.Generator().manual_seed(nq * 1000 + k)
     s = torch.randn(nq, n, generator=g)
@@ -188,6 +190,21 @@ def test_topk_matches_sort(evdr, cuda, nq, n, k):
     rv, ri = _oracle_topk(s.numpy(), k)
     assert np.array_equal(ids.cpu().numpy(), ri)
     assert np.array_equal(vals.cpu().numpy(), rv)
+
+
+def test_topk_minus_inf_scores_and_register_list_edge_cases(evdr, cuda):
+    """k <= 32 takes the register-list kernel: -inf scores are real candidates (absent pages of a result
+    dict are -inf, evaluator path), all-equal rows resolve by column, descending rows insert at the tail and
+    ascending rows at the head every time."""
+    n = 700
+    rows = [torch.full((n,), float("-inf")), torch.zeros(n), torch.arange(n, 0, -1).float(),
+            torch.arange(n).float(), torch.cat([torch.full((n - 3,), float("-inf")), torch.tensor([1.0, 3.0, 2.0])])]
+    s = torch.stack(rows)
+    for k in (1, 10, 32):
+        vals, ids = evdr.top_k(s.to(cuda), k)
+        rv, ri = _oracle_topk(s.numpy(), k)
+        assert np.array_equal(ids.cpu().numpy(), ri), k
+        assert np.array_equal(vals.cpu().numpy(), rv), k
 
 
 def test_topk_tie_rank_and_offset(evdr, cuda):
