@@ -18,12 +18,8 @@ from ._lib import CHUNK, TC_DIM, TC_LQ, TC_LQ_MAX
 def _mask_u8(mask: torch.Tensor) -> torch.Tensor:
     """Masks of any dtype -> contiguous uint8, non-zero = valid (reference `.bool()`, :179-180)."""
     if mask.dtype == torch.bool:
-        m = mask.contiguous().view(torch.uint8)
-    elif mask.dtype == torch.uint8:
-        m = (mask != 0).contiguous().view(torch.uint8)
-    else:
-        m = (mask != 0).contiguous().view(torch.uint8)
-    return m
+        return mask.contiguous().view(torch.uint8)
+    return (mask != 0).contiguous().view(torch.uint8)
 
 
 def _float_operand(t: torch.Tensor) -> torch.Tensor:
