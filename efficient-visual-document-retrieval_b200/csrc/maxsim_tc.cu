@@ -50,19 +50,26 @@ struct TcParams {
   int32_t* argmax;            // AM variant: [np, nq*lq] winning packed slot per (page, query token)
   int lq;                     // AM variant: real query length (rows >= lq are padding)
   int* sched;                 // dynamic scheduler: global item counter (zeroed per launch); CG2: unused
+  const __nv_bfloat16* qb;    // TA variant: packed queries [nq, 32, 128] in global memory (staged to TMEM)
 };
 
 // KB = number of 128-wide K blocks of the operands: 1 = plain bf16; 3 = the bf16x3 split
 // A = [Qhi | Qhi | Qlo], B = [Phi | Plo | Phi] whose K = 384 contraction is Qhi.Phi + Qhi.Plo + Qlo.Phi,
 // i.e. the fp32 dot product up to the dropped Qlo.Plo term (~2^-18 relative) -- the high-fidelity mode
-template <int R, int BN, int STAGES, bool CG2, int KB = 1, bool SP = false, int EW = 4>
+// TA: the resident query tiles (A operand) live in TENSOR MEMORY instead of shared memory: the epilogue
+// warps copy their query's 32 token rows global -> registers -> TMEM (tcgen05.st) at every item change and
+// the MMAs take A from TMEM.  Shared-memory operand reads drop from 96 to 64 B/clk per SM (only the page
+// tile is read), and the 64-96 KB the query tiles occupied go to a deeper page-tile ring.  TMEM holds two
+// BN = 192-column accumulators (384) + R = 2 query tiles of 64 columns (128) = 512 columns.
+template <int R, int BN, int STAGES, bool CG2, int KB = 1, bool SP = false, int EW = 4, bool TA = false>
 struct TcCfg {
   static constexpr int B_ROWS = CG2 ? BN / 2 : BN;          // page tokens held by this CTA per stage
   static constexpr int KSUB = 2 * KB;                        // 64-wide K sub-tiles per operand tile
   static constexpr int B_HALF_BYTES = B_ROWS * 64 * 2;       // one 64-wide K sub-tile
   static constexpr int B_STAGE_BYTES = KSUB * B_HALF_BYTES;
   static constexpr int A_TILE_BYTES = KSUB * A_HALF_BYTES;
-  static constexpr int A_BYTES = R * A_TILE_BYTES;
+  static constexpr int A_BYTES = TA ? 0 : R * A_TILE_BYTES;
+  static constexpr int A_COL = 2 * BN;                       // TA: first TMEM column of query tile 0
   static constexpr int B_BYTES = STAGES * B_STAGE_BYTES;
   static constexpr int BAR_OFF = A_BYTES + B_BYTES;
   // barriers: full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2], tmem ptr,
@@ -84,17 +91,22 @@ struct TcCfg {
 // EW = number of epilogue warps: 4 (one group, TMEM buffers alternate per pass) or 8 (two groups of 4;
 // requires R == 2: pass (tile t, query tile r) always uses TMEM buffer r and is drained by group r, so
 // each group owns one query tile's running state and has two MMA periods per pass).
-template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4>
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4,
+          bool TA = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                  const TcParams prm) {
-  using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW>;
+  using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW, TA>;
+  static_assert(!TA || (!CG2 && !AM && KB == 1 && 2 * BN + R * 64 <= 512),
+                "TMEM-resident query tiles: single-CTA bf16 scoring flavour, accumulators + tiles within 512 columns");
   constexpr int A_TILE_BYTES = S::A_TILE_BYTES;
   constexpr int KSUB = S::KSUB;
-  constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                            : (2 * BN <= 256) ? 256 : 512;
+  constexpr int TMEM_NEED = 2 * BN + (TA ? R * 64 : 0);
+  constexpr int TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 : (TMEM_NEED <= 128) ? 128
+                            : (TMEM_NEED <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
+  static_assert((BN / 32) % 2 == 0, "the drain loop handles 32-column groups in pairs");
   static_assert(EW == 4 || (EW == 8 && R == 2 && !CG2), "8 epilogue warps need R == 2, single-CTA");
   constexpr uint32_t IDESC = make_idesc_bf16(CG2 ? 256 : 128, BN);
   constexpr int CH_PER_TILE = BN / EVDR_CHUNK;
@@ -130,7 +142,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapP);
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_full, TA ? EW : 1);       // TA: every epilogue warp arrives after staging its rows
     mbar_init(bar_a_empty, 1);
     // tmem_empty lives in the leader: 4 epilogue warps of each CTA of the pair arrive on it
     for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full(b), 1); mbar_init(bar_t_empty(b), CG2 ? 8 : 4); }
@@ -185,7 +197,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         const int c0 = prm.chunk_off[p0], c1 = prm.chunk_off[p1];
         const int ntile = ((c1 - c0) * EVDR_CHUNK + BN - 1) / BN;
         const int rc = passes_in_group(g);
-        if (g != cur_g) {
+        if (!TA && g != cur_g) {
           if (a_loads > 0) mbar_wait(bar_a_empty, (a_loads - 1) & 1);
           // out-of-range query tiles are zero-filled by TMA and still count their bytes
           if (rank == 0) mbar_expect_tx(bar_a_full, (CG2 ? 2 : 1) * rc * A_TILE_BYTES);
@@ -247,7 +259,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         const int ntile = ((c1 - c0) * EVDR_CHUNK + BN - 1) / BN;
         const int rc = passes_in_group(g);
         if (g != cur_g) {
-          if (cur_g != -1) commit(bar_a_empty);  // previous A tiles free once their MMAs retire
+          if (!TA && cur_g != -1) commit(bar_a_empty);  // previous A tiles free once their MMAs retire
           mbar_wait(bar_a_full, a_phase);
           a_phase ^= 1;
           tc_fence_after();
@@ -269,6 +281,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
               const uint64_t da = make_sw128_desc(a_base + (k >> 2) * A_HALF_BYTES + (k & 3) * 32);
               const uint64_t db = make_sw128_desc(b_base + (k >> 2) * S::B_HALF_BYTES + (k & 3) * 32);
               if constexpr (CG2) mma_bf16_ss_cg2(d_tmem, da, db, IDESC, k > 0);
+              else if constexpr (TA) mma_bf16_ts(d_tmem, tmem_base + S::A_COL + r * 64 + k * 8, db, IDESC, k > 0);
               else mma_bf16_ss(d_tmem, da, db, IDESC, k > 0);
             }
             commit(bar_t_full(buf));
@@ -333,6 +346,32 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
           const bool ok = (r < rc) && (tile < group_start(g) + group_size(g)) && (q < prm.nq);
           qidx[r] = ok ? q : -1;
           qm[r] = ok ? (float)prm.qmask32[(size_t)q * EVDR_TC_LQ + lane] : 0.f;
+          if constexpr (TA) {
+            // stage this warp's query (32 token rows = TMEM lanes of its quadrant) as query tile r.  The warp
+            // has drained the last pass that read tile r, so the columns are free; the other tile may still
+            // be in use by a running MMA and is not touched.
+            if (r < rc && (EW == 4 || r == egrp)) {
+              uint32_t a[64];
+              if (ok) {
+                const uint4* src = reinterpret_cast<const uint4*>(prm.qb + ((size_t)q * EVDR_TC_LQ + lane) * EVDR_TC_DIM);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const uint4 v = __ldg(src + i);
+                  a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) a[i] = 0u;
+              }
+              tmem_st64(t_lane + S::A_COL + r * 64, a);
+            }
+          }
+        }
+        if constexpr (TA) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_full);
         }
         cur_g = g;
       }
@@ -564,16 +603,18 @@ static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uin
   return EVDR_OK;
 }
 
-template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4>
+template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4,
+          bool TA = false>
 static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens,
                      TcParams prm, cudaStream_t st) {
-  using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW>;
+  using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW, TA>;
+  prm.qb = static_cast<const __nv_bfloat16*>(Qb);
   CUtensorMap tmQ, tmP;
   int rc = encode_2d_bf16(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, 128, KB, "queries");
   if (rc != EVDR_OK) return rc;
   rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, KB, "page tokens");
   if (rc != EVDR_OK) return rc;
-  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP, EW>;
+  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP, EW, TA>;
   if ((size_t)S::TOTAL > h->smem_optin)
     return set_error(EVDR_ERR_UNSUPPORTED, "tensor-core kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -707,6 +748,11 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     if (R == 2) return launch_tc<2, 256, 5, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 3) return launch_tc<3, 256, 4, true>(h, Qb, tokens, n_tokens, prm, st);
     return launch_tc<4, 256, 3, true>(h, Qb, tokens, n_tokens, prm, st);
+  }
+  // query tiles in TMEM (EVDR_TC_MODE=ta): 192-token page tiles, 4-stage ring
+  if (mode && strcmp(mode, "ta") == 0 && (short_pages || want_ew8)) {
+    if (short_pages) return launch_tc<2, 192, 4, false, false, 1, true, 8, true>(h, Qb, tokens, n_tokens, prm, st);
+    return launch_tc<2, 192, 4, false, false, 1, false, 8, true>(h, Qb, tokens, n_tokens, prm, st);
   }
   if (short_pages) return launch_tc<2, 256, 2, false, false, 1, true, 8>(h, Qb, tokens, n_tokens, prm, st);
   if (want_ew8) return launch_tc<2, 256, 2, false, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);

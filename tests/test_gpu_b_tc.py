@@ -184,3 +184,20 @@ def test_host_corpus_streaming_equals_resident_scoring(evdr, cuda, nq, ppc):
     assert hc.score(Q, qm, out=out) is out and torch.equal(out, want)      # staging buffers reused
     with pytest.raises(ValueError):
         evdr.HostCorpus(corpus.cpu(), cuda)                                   # not pinned
+
+
+@pytest.mark.parametrize("nq,lp,npg", [(61, 1030, 150), (64, 1030, 97), (100, 1030, 150), (131, 1030, 60),
+                                       (5, 64, 3000), (40, 64, 3000), (100, 333, 700), (9, 16, 500), (64, 208, 900)])
+def test_tmem_resident_query_tiles_vs_exact_kernel(evdr, cuda, nq, lp, npg, monkeypatch):
+    """EVDR_TC_MODE=ta: the query tiles (A operand) are staged into TENSOR MEMORY by the epilogue warps and the
+    MMAs read A from TMEM (192-token page tiles, 4-stage ring) -- long pages with the tree / segment fold and
+    short pages with the end-mask epilogue, partial last tiles and groups included."""
+    monkeypatch.setenv("EVDR_TC_MODE", "ta")
+    P, pm = evdr.synth.make_pages(npg, lp, seed=300 + nq, device=cuda, n_holes=min(4, lp - 1), empty_frac=0.02,
+                                  min_len=max(1, lp // 3))
+    Q, qm, rel = evdr.synth.make_queries(P, pm, nq, 32, seed=400 + nq, sigma=3.0, min_len=8, drop=0.1)
+    evdr.retrieval.clear_pack_cache()
+    got = evdr.PackedPages.from_padded(P, pm, varlen=True).score(Q, qm)
+    ref = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
+    U.assert_scores_close(got.cpu().numpy(), ref.cpu().numpy())
+    assert got.abs().max() > 1.0
