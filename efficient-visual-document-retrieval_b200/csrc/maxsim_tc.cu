@@ -702,7 +702,13 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   const bool short_pages = two_groups_ok && prm.nqt >= 2 && (avg_chunks < 32.0 || force_sp8);
   const bool want_ew8 = two_groups_ok && !short_pages &&
                         (prm.nqt >= 16 || (mode && strcmp(mode, "ew8") == 0 && prm.nqt >= 2));
-  if (short_pages || want_ew8) { R = 2; tpg = 2; }
+  // Query tiles in TMEM + a 4-stage ring of 192-token page tiles: the default for exactly two query tiles
+  // (5-8 queries) on long pages, where the scan is HBM-bound and the deeper ring is worth 1-12 % (4.9-5.8 ms
+  // vs 5.2-5.9 ms per 100k pages, profiles/r1g_tmem_resident_query_tiles.log); everywhere else it measured
+  // equal or slower and stays opt-in (EVDR_TC_MODE=ta).
+  const bool want_ta = two_groups_ok && prm.nqt >= 2 &&
+                       ((mode && strcmp(mode, "ta") == 0) || (!mode && prm.nqt == 2 && !short_pages));
+  if (short_pages || want_ew8 || want_ta) { R = 2; tpg = 2; }
   const int n_qgroups = (prm.nqt + tpg - 1) / tpg;
   const int units = pair ? h->sm_count / 2 : h->sm_count;
   int ppi = pages_per_item;
@@ -750,7 +756,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     return launch_tc<4, 256, 3, true>(h, Qb, tokens, n_tokens, prm, st);
   }
   // query tiles in TMEM (EVDR_TC_MODE=ta): 192-token page tiles, 4-stage ring
-  if (mode && strcmp(mode, "ta") == 0 && (short_pages || want_ew8)) {
+  if (want_ta) {
     if (short_pages) return launch_tc<2, 192, 4, false, false, 1, true, 8, true>(h, Qb, tokens, n_tokens, prm, st);
     return launch_tc<2, 192, 4, false, false, 1, false, 8, true>(h, Qb, tokens, n_tokens, prm, st);
   }
