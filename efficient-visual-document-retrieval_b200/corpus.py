@@ -249,6 +249,7 @@ class HostCorpus:
         if pages_per_chunk <= 0:                       # ~2 GiB per staging buffer
             pages_per_chunk = max(1, (2 << 30) // (L * d * 2))
         self.ppc = min(int(pages_per_chunk), npg)
+        self.ramp = 1.18
         self._stage = [torch.empty((self.ppc, L, d), dtype=torch.bfloat16, device=self.device) for _ in range(2)]
         cpp = L // CHUNK
         self._chunk_off = torch.arange(0, (self.ppc + 1) * cpp, cpp, dtype=torch.int32, device=self.device)
@@ -265,12 +266,15 @@ class HostCorpus:
         full = torch.empty((rows, self.n_pages), dtype=torch.float32, device=dev) if (out is None or G > 1) else out
         main = torch.cuda.current_stream(dev)
         cs = self._copy_stream
-        # chunk sizes ramp up (ppc/16, ppc/8, ... ppc): only the FIRST copy is exposed, so it is kept small
-        bounds, c, step = [0], 0, max(1, self.ppc // 16)
+        # Chunk sizes ramp up from ppc/32 to ppc: only the FIRST copy is exposed, so it is kept small.  The
+        # growth factor must stay below (link rate / scoring rate), else the copy of chunk i+1 outlasts the
+        # scoring of chunk i all the way up the ramp (a 2x ramp exposed ~25 ms of a 0.6 s step): 1.18 covers
+        # scoring down to ~47 GB/s of page bytes per second on a 55 GB/s link.
+        bounds, c, step = [0], 0, float(max(1, self.ppc // 32))
         while c < self.n_pages:
-            c = min(self.n_pages, c + step)
+            c = min(self.n_pages, c + int(step))
             bounds.append(c)
-            step = min(self.ppc, step * 2)
+            step = min(float(self.ppc), step * self.ramp)
         # the staging buffers may still be read by a previous call on this stream
         cs.wait_stream(main)
         for i in range(len(bounds) - 1):
