@@ -176,6 +176,54 @@ class PackedPages:
         return PackedPages(tokens, chunk_off, npg, total, page_offset, k_blocks)
 
     @staticmethod
+    def from_tensor_list(pages, *, device, extra_zero_token=None, normalize: bool = False,
+                         page_offset: int = 0, k_blocks: int = 1) -> "PackedPages":
+        """Pack a list of (Li, 128) torch tensors (any float dtype, any device) without masks: one
+        concatenation, at most one host->device copy, one ragged pack on the device -- no per-page copies and
+        no padded (N, Lmax, D) intermediate.  extra_zero_token[i] appends one all-zero token to page i (how the
+        list scorer's zero LEFT padding takes part in the max, evaluator/retrieval.py:30-45,136)."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.EvdrError("from_tensor_list packs on the GPU: this package has no CPU fallback")
+        npg = len(pages)
+        lens = [int(p.shape[0]) for p in pages]
+        if extra_zero_token is None:
+            extra_zero_token = [False] * npg
+        if len({p.device for p in pages}) > 1:
+            pages = [p.to(device) for p in pages]
+        parts, zero = [], None
+        for p, z in zip(pages, extra_zero_token):
+            parts.append(p.reshape(-1, TC_DIM))
+            if z:
+                if zero is None or zero.device != p.device or zero.dtype != p.dtype:
+                    zero = torch.zeros((1, TC_DIM), dtype=p.dtype, device=p.device)
+                parts.append(zero)
+        flat = torch.cat(parts, dim=0).to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        lens_t = torch.tensor([l + (1 if z else 0) for l, z in zip(lens, extra_zero_token)], dtype=torch.int64)
+        off = torch.zeros(npg + 1, dtype=torch.int64)
+        torch.cumsum(lens_t, 0, out=off[1:])
+        total_tok = int(off[-1])
+        max_len = int(lens_t.max()) if npg else 1
+        off_d = off.to(device, non_blocking=True)
+        if total_tok == 0:
+            flat = torch.zeros((1, TC_DIM), dtype=torch.float32, device=device)
+        mask_d = torch.ones(max(1, total_tok), dtype=torch.uint8, device=device)
+        lib = _lib.load()
+        h = _lib.handle(device)
+        st = _lib.stream_ptr(device)
+        chunk_off = torch.empty(npg + 1, dtype=torch.int32, device=device)
+        _lib.check(lib.evdr_pack_plan_ragged(h, mask_d.data_ptr(), off_d.data_ptr(), npg, chunk_off.data_ptr(), st),
+                   "evdr_pack_plan_ragged")
+        # every page has at least one chunk and ceil(len/16) otherwise: known on the host, no device read
+        total = sum(max(1, (int(l) + CHUNK - 1) // CHUNK) for l in lens_t.tolist())
+        tokens = torch.empty((total * CHUNK, TC_DIM * k_blocks), dtype=torch.bfloat16, device=device)
+        _lib.check(lib.evdr_pack_pages_ragged(h, flat.data_ptr(), _lib.EVDR_F32, mask_d.data_ptr(), off_d.data_ptr(),
+                                              chunk_off.data_ptr(), npg, max(1, max_len), TC_DIM,
+                                              1 if normalize else 0, k_blocks, tokens.data_ptr(), st),
+                   "evdr_pack_pages_ragged")
+        return PackedPages(tokens, chunk_off, npg, total, page_offset, k_blocks)
+
+    @staticmethod
     def from_uniform_tokens(tokens: torch.Tensor, page_offset: int = 0) -> "PackedPages":
         """Zero-copy view of an all-valid bf16 corpus (np, L, 128) with L % 16 == 0."""
         _lib.require_cuda(tokens, "tokens")

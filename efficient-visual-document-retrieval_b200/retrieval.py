@@ -364,28 +364,36 @@ class BaseVisualRetrieverProcessor(ABC):
         qs = [q.unsqueeze(0) if q.ndim == 1 else q for q in qs]
         ps = [p.unsqueeze(0) if p.ndim == 1 else p for p in ps]
         d = qs[0].shape[-1]
-        lq = max(q.shape[0] for q in qs)
-        Q = torch.zeros((len(qs), lq, d), dtype=torch.float32, device=device)
-        qm = torch.zeros((len(qs), lq), dtype=torch.bool, device=device)
-        for i, q in enumerate(qs):
-            Q[i, : q.shape[0]] = q.to(device=device, dtype=torch.float32)
-            qm[i, : q.shape[0]] = True
+        qlens = [q.shape[0] for q in qs]
+        lq = max(qlens)
+        # queries: one pad_sequence + one copy (zero RIGHT padding with a mask == the reference's zero left
+        # padding: padded query tokens add 0 either way)
+        if len({q.device for q in qs}) > 1:            # mixed devices: the reference moves each one (:38-43)
+            qs = [q.to(device) for q in qs]
+        Q = torch.nn.utils.rnn.pad_sequence([q.to(torch.float32) for q in qs], batch_first=True).to(device)
+        qm = (torch.arange(lq)[None, :] < torch.tensor(qlens)[:, None]).to(device)
         lens = [p.shape[0] for p in ps]
         padded = []
         for j0 in range(0, len(ps), batch_size):
             blk = lens[j0:j0 + batch_size]
             mx = max(blk)
             padded.extend(l < mx for l in blk)
-        lp = max(l + (1 if pad else 0) for l, pad in zip(lens, padded))
-        P = torch.zeros((len(ps), lp, d), dtype=torch.float32, device=device)
-        pm = torch.zeros((len(ps), lp), dtype=torch.bool, device=device)
-        for j, p in enumerate(ps):
-            P[j, : lens[j]] = p.to(device=device, dtype=torch.float32)
-            pm[j, : lens[j] + (1 if padded[j] else 0)] = True   # the extra valid slot is a zero token
         with torch.no_grad():
             if d == TC_DIM and lq <= TC_LQ_MAX and os.environ.get("EVDR_PRECISION", "bf16") != "fp32":
-                scores = PackedPages.from_padded(P, pm, varlen=True).score(Q, qm)
+                # pages: one concatenation, one copy, one ragged pack; a page shorter than its block's longest
+                # gets one extra all-zero token (the reference's padding zeros take part in the max)
+                pk = PackedPages.from_tensor_list(ps, device=device, extra_zero_token=padded)
+                scores = pk.score(Q, qm)
             else:
+                lp = max(l + (1 if pad else 0) for l, pad in zip(lens, padded))
+                if len({p.device for p in ps}) > 1:
+                    ps = [p.to(device) for p in ps]
+                P = torch.nn.utils.rnn.pad_sequence([p.to(torch.float32) for p in ps], batch_first=True)
+                if P.shape[1] < lp:
+                    P = torch.nn.functional.pad(P, (0, 0, 0, lp - P.shape[1]))
+                P = P.to(device)
+                plen = torch.tensor([l + (1 if pad else 0) for l, pad in zip(lens, padded)])
+                pm = (torch.arange(lp)[None, :] < plen[:, None]).to(device)   # the extra valid slot is a zero token
                 scores = maxsim_exact(Q, P, qm, pm)
         scores = scores.cpu()
         assert scores.shape[0] == len(qs), f"Expected {len(qs)} scores, got {scores.shape[0]}"

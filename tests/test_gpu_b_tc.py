@@ -146,6 +146,33 @@ def test_list_scorer_matches_reference(evdr, cuda):
         P.score_multi_vector(qs, [])
 
 
+@pytest.mark.parametrize("where,dtype,d", [("cuda", torch.float32, 128), ("cpu", torch.bfloat16, 128),
+                                            ("mixed", torch.float32, 128), ("cpu", torch.float32, 64)])
+def test_list_scorer_input_forms(evdr, cuda, where, dtype, d):
+    """Lists of GPU tensors, bf16 tensors, lists spread over devices and d != 128 (exact kernels) against the
+    oracle's restatement of evaluator/retrieval.py:101-150 (itself pinned to the reference's outputs)."""
+    from oracle import maxsim_oracle as mo
+    g = torch.Generator().manual_seed(d)
+    # bf16-representable values: both sides see identical inputs (the tensor-core path rounds to bf16)
+    qs = [torch.nn.functional.normalize(torch.randn(int(n), d, generator=g), dim=-1).bfloat16().to(dtype)
+          for n in torch.randint(3, 40, (9,), generator=g)]
+    ps = [torch.nn.functional.normalize(torch.randn(int(n), d, generator=g), dim=-1).bfloat16().to(dtype)
+          for n in torch.randint(1, 90, (23,), generator=g)]
+    want = mo.maxsim_list([q.float().numpy() for q in qs], [p.float().numpy() for p in ps], batch_size=5)
+    if where == "cuda":
+        qs, ps = [q.to(cuda) for q in qs], [p.to(cuda) for p in ps]
+    elif where == "mixed":
+        qs = [q.to(cuda) if i % 2 else q for i, q in enumerate(qs)]
+        ps = [p.to(cuda) if i % 3 else p for i, p in enumerate(ps)]
+    got = evdr.BaseVisualRetrieverProcessor.score_multi_vector(qs, ps, batch_size=5, device=str(cuda))
+    assert got.device.type == "cpu" and got.shape == (9, 23)
+    U.assert_scores_close(got.numpy(), want)
+    # a stacked (N, L, D) tensor is a valid "list" too (the reference iterates over it)
+    st_q = torch.stack([q[:3] for q in qs if q.device == qs[1].device][:3])
+    got2 = evdr.BaseVisualRetrieverProcessor.score_multi_vector(st_q, ps, batch_size=128, device=str(cuda))
+    assert got2.shape == (st_q.shape[0], 23)
+
+
 def test_search_api(evdr, cuda):
     P, pm = evdr.synth.make_pages(400, 64, seed=9, device=cuda, n_holes=0, empty_frac=0.0)
     Q, qm, rel = evdr.synth.make_queries(P, pm, 12, 32, seed=10, sigma=1.0)
