@@ -225,6 +225,43 @@ def clear_pack_cache() -> None:
     _PACK_CACHE.clear()
 
 
+class _ScoreMatrix(torch.Tensor):
+    """The (Q, P) fp32 score tensor of a no-grad call: an ordinary CUDA tensor for every torch op (ops on
+    it return plain tensors, like nn.Parameter), except that SCALAR indexing ``scores[qi, di]`` is served
+    from a pinned host mirror that is filled with one device->host copy on first use.
+
+    Why: every evaluation of the reference builds its results dict with ``float(scores[qi, di].item())``
+    for all Q x P pairs (mainv2_iter_listwise.py:312-318) -- on a GPU tensor that is Q*P device
+    synchronisations (250 000 for DocVQA, seconds per evaluation).  With the mirror the
+    same unmodified loop does one copy and Q*P host reads.  The mirror is keyed on the tensor's in-place
+    version counter, so writes through any torch op invalidate it."""
+
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    @staticmethod
+    def wrap(t: torch.Tensor) -> "torch.Tensor":
+        if os.environ.get("EVDR_HOST_MIRROR", "1") == "0":
+            return t
+        out = torch.Tensor._make_subclass(_ScoreMatrix, t)
+        out._evdr_mirror = None
+        return out
+
+    def _host(self):
+        m = getattr(self, "_evdr_mirror", None)
+        if m is None or m[0] != self._version:
+            plain = torch.Tensor._make_subclass(torch.Tensor, self)
+            host = torch.empty(plain.shape, dtype=plain.dtype, pin_memory=True)
+            host.copy_(plain)                       # synchronous for pinned destinations: one sync in total
+            m = (self._version, host)
+            self._evdr_mirror = m
+        return m[1]
+
+    def __getitem__(self, idx):
+        if (type(idx) is tuple and len(idx) == self.dim() and all(type(i) is int for i in idx)):
+            return self._host()[idx]
+        return torch.Tensor._make_subclass(torch.Tensor, self)[idx]
+
+
 def score_multi_vector_masked(
     Q: torch.Tensor,        # (Q, Lq, D)
     P: torch.Tensor,        # (P, Lp, D)
@@ -239,7 +276,10 @@ def score_multi_vector_masked(
         out[q,c] = has[c] * sum_n qmask[q,n] * max_m ( pmask[c,m] ? <Q[q,n],P[c,m]> : -1e4 )
 
     Returns a new fp32 (Q, P) tensor on the inputs' device.  ``chunk_p`` is accepted and ignored
-    (the reference's outputs do not depend on it and nothing is materialised here).
+    (the reference's outputs do not depend on it and nothing is materialised here).  Results that carry
+    no gradient are ``_ScoreMatrix`` tensors: plain CUDA tensors whose scalar reads ``scores[q, c].item()``
+    (the reference's evaluation loop, mainv2_iter_listwise.py:312-318) come from a host mirror filled by
+    ONE device->host copy instead of Q*P synchronisations (EVDR_HOST_MIRROR=0 disables it).
 
     precision=None | "bf16": tcgen05 path (bf16 operands, fp32 accumulation) whenever D == 128 and
     Lq <= 32.  Calls that need a gradient use the same tensor-core kernel to FIND the winning page
@@ -264,11 +304,12 @@ def score_multi_vector_masked(
     precision = precision or os.environ.get("EVDR_PRECISION", "bf16")
     needs_grad = torch.is_grad_enabled() and (Q.requires_grad or P.requires_grad)
     if precision == "fp32" or d != TC_DIM or lq > TC_LQ_MAX:
-        return maxsim_exact(Q, P, qmask, pmask)
+        out = maxsim_exact(Q, P, qmask, pmask)
+        return out if out.requires_grad else _ScoreMatrix.wrap(out)
     if precision == "bf16x3" and not needs_grad:
         # high-fidelity tensor-core mode for operands that are not bf16-representable
         with torch.no_grad():
-            return PackedPages.from_padded(P.detach(), pmask, k_blocks=3).score(Q.detach(), qmask)
+            return _ScoreMatrix.wrap(PackedPages.from_padded(P.detach(), pmask, k_blocks=3).score(Q.detach(), qmask))
     if needs_grad:
         # training: tensor-core search + fp32 rescoring of the winners, backward through the same indices
         Qf, qm8 = _float_operand(Q), _mask_u8(qmask)
@@ -280,7 +321,7 @@ def score_multi_vector_masked(
             qm8 = torch.nn.functional.pad(qm8, (0, pad))
         return _MaxSimRescoreFn.apply(Qf, _float_operand(P), qm8, _mask_u8(pmask))
     with torch.no_grad():
-        return _packed_for(P.detach(), pmask).score(Q.detach(), qmask)   # lq > 32: scored as 32-token groups
+        return _ScoreMatrix.wrap(_packed_for(P.detach(), pmask).score(Q.detach(), qmask))   # lq > 32: 32-token groups
 
 
 class TeacherScoreTable:

@@ -320,3 +320,29 @@ def test_training_step_captured_in_cuda_graph(evdr, cuda):
     assert torch.equal(torch.stack(eager), torch.stack(replayed))
     assert torch.equal(pe.detach(), pg.detach())
     assert bool(torch.isfinite(torch.stack(eager)).all()) and not torch.equal(pe.detach(), init), "the student was trained"
+
+
+def test_reference_eval_loop_reads_scores_from_host_mirror(evdr, cuda):
+    """The reference builds its results dict with float(scores[qi, di].item()) for every pair
+    (mainv2_iter_listwise.py:312-318).  No-grad results are ordinary CUDA tensors whose scalar reads come from
+    a host mirror (one copy instead of Q*P device synchronisations); everything else behaves like a Tensor."""
+    import time
+    P, pm = evdr.synth.make_pages(300, 64, seed=31, device=cuda, n_holes=2, empty_frac=0.01, min_len=20)
+    Q, qm, _ = evdr.synth.make_queries(P, pm, 200, 32, seed=32, sigma=2.0, min_len=6, drop=0.1)
+    with torch.no_grad():
+        scores = evdr.score_multi_vector_masked(Q, P, qm, pm, chunk_p=64)
+    assert isinstance(scores, torch.Tensor) and scores.is_cuda and scores.dtype == torch.float32
+    plain = scores + 0                                     # ops return plain tensors
+    assert type(plain) is torch.Tensor and type(scores[3]) is torch.Tensor and type(scores[:, 1:5]) is torch.Tensor
+    t0 = time.perf_counter()
+    results = {str(qi): {str(di): float(scores[qi, di].item()) for di in range(scores.shape[1])}
+               for qi in range(scores.shape[0])}
+    dt = time.perf_counter() - t0
+    host = plain.cpu()
+    assert all(results[str(q)][str(c)] == float(host[q, c]) for q in (0, 7, 199) for c in (0, 150, 299))
+    assert dt < 3.0, f"{dt:.2f} s for 60 000 scalar reads: the mirror is not being used"
+    scores.mul_(2.0)                                       # an in-place write invalidates the mirror
+    assert float(scores[7, 150].item()) == 2.0 * float(host[7, 150])
+    # results that carry a gradient are untouched
+    Pg = P.float().requires_grad_(True)
+    assert type(evdr.score_multi_vector_masked(Q[:4], Pg, qm[:4], pm)) is torch.Tensor
