@@ -133,7 +133,7 @@ class _MaxSimRescoreFn(torch.autograd.Function):
         h = _lib.handle(dev)
         st = _lib.stream_ptr(dev)
         R = nq * lq
-        if 4 * R * npg <= _EXACT_WS_BYTES:
+        if 4 * R * npg <= _EXACT_WS_BYTES and npg <= 65535:
             # one library call (evdr_maxsim_train_fwd): both packs, the search, the rescoring and the sum
             am = torch.empty((npg, R), dtype=torch.int32, device=dev)
             out = torch.empty((nq, npg), dtype=torch.float32, device=dev)

@@ -346,3 +346,20 @@ def test_reference_eval_loop_reads_scores_from_host_mirror(evdr, cuda):
     # results that carry a gradient are untouched
     Pg = P.float().requires_grad_(True)
     assert type(evdr.score_multi_vector_masked(Q[:4], Pg, qm[:4], pm)) is torch.Tensor
+
+
+def test_gradient_call_over_more_than_65535_pages(evdr, cuda):
+    """A single query against 70 000 short student pages: beyond the page count one rescoring launch covers,
+    so the composed path (page blocks) must take over transparently."""
+    g = torch.Generator(device=cuda).manual_seed(9)
+    npg, ls = 70_000, 5
+    P = torch.nn.functional.normalize(torch.randn(npg, ls, 128, generator=g, device=cuda), dim=-1)
+    pm = torch.rand(npg, ls, generator=g, device=cuda) > 0.2
+    Q = torch.nn.functional.normalize(torch.randn(1, 7, 128, generator=g, device=cuda), dim=-1)
+    qm = torch.ones(1, 7, dtype=torch.bool, device=cuda)
+    Pg = P.clone().requires_grad_(True)
+    out = evdr.score_multi_vector_masked(Q, Pg, qm, pm)
+    out.sum().backward()
+    ref = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-5)
+    assert Pg.grad.shape == P.shape and Pg.grad[~pm].abs().max() == 0
