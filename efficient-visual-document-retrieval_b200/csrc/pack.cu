@@ -268,6 +268,84 @@ l2norm_bwd_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask,
   }
 }
 
+// d == 128 (ColPali): one float4 per lane is a whole token, so a warp keeps TPW tokens in registers (TPW
+// independent 512-byte loads in flight, no second read of x), reduces their sums interleaved and streams the
+// results out; grid-stride over token groups.
+constexpr int L2N_TPW = 4;
+
+__global__ void __launch_bounds__(256)
+l2norm_fwd128_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask, long long n_tok,
+                     float* __restrict__ Y) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long t0 = warp0 * L2N_TPW; t0 < n_tok; t0 += nwarp * L2N_TPW) {
+    float4 v[L2N_TPW];
+    float ss[L2N_TPW];
+#pragma unroll
+    for (int u = 0; u < L2N_TPW; ++u) {
+      const long long t = t0 + u;
+      const bool valid = t < n_tok && (mask == nullptr || mask[t] != 0);
+      v[u] = valid ? __ldcs(reinterpret_cast<const float4*>(X + t * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss[u] = v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < L2N_TPW; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+#pragma unroll
+    for (int u = 0; u < L2N_TPW; ++u) {
+      const long long t = t0 + u;
+      if (t >= n_tok) break;
+      const float inv = 1.f / (sqrtf(ss[u]) + 1e-12f);
+      __stcs(reinterpret_cast<float4*>(Y + t * 128) + lane,
+             make_float4(v[u].x * inv, v[u].y * inv, v[u].z * inv, v[u].w * inv));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+l2norm_bwd128_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask,
+                     const float* __restrict__ gY, long long n_tok, float* __restrict__ gX) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long t0 = warp0 * L2N_TPW; t0 < n_tok; t0 += nwarp * L2N_TPW) {
+    float4 v[L2N_TPW], w[L2N_TPW];
+    float ss[L2N_TPW], xg[L2N_TPW];
+    bool ok[L2N_TPW];
+#pragma unroll
+    for (int u = 0; u < L2N_TPW; ++u) {
+      const long long t = t0 + u;
+      ok[u] = t < n_tok && (mask == nullptr || mask[t] != 0);
+      v[u] = ok[u] ? __ldcs(reinterpret_cast<const float4*>(X + t * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      w[u] = ok[u] ? __ldcs(reinterpret_cast<const float4*>(gY + t * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss[u] = v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+      xg[u] = v[u].x * w[u].x + v[u].y * w[u].y + v[u].z * w[u].z + v[u].w * w[u].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < L2N_TPW; ++u) {
+        ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+        xg[u] += __shfl_xor_sync(0xffffffffu, xg[u], o);
+      }
+#pragma unroll
+    for (int u = 0; u < L2N_TPW; ++u) {
+      const long long t = t0 + u;
+      if (t >= n_tok) break;
+      const float n = sqrtf(ss[u]);
+      const float a = 1.f / (n + 1e-12f);
+      const float b = (n > 0.f) ? xg[u] * a * a / n : 0.f;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[u])
+        r = make_float4(w[u].x * a - v[u].x * b, w[u].y * a - v[u].y * b, w[u].z * a - v[u].z * b,
+                        w[u].w * a - v[u].w * b);
+      __stcs(reinterpret_cast<float4*>(gX + t * 128) + lane, r);
+    }
+  }
+}
+
 }  // namespace evdr
 
 using namespace evdr;
@@ -386,7 +464,13 @@ int evdr_l2norm_fwd(evdr_handle* h, const float* X, const uint8_t* mask, int64_t
   EVDR_REQUIRE_HANDLE(h);
   EVDR_CHECK_ARG(X && Y && n_tok >= 1 && d >= 4 && d % 4 == 0, "evdr_l2norm_fwd: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  l2norm_fwd_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(X, mask, n_tok, d, Y);
+  if (d == 128) {
+    const long long groups = (n_tok + 8 * L2N_TPW - 1) / (8 * L2N_TPW);
+    const long long cap = (long long)h->sm_count * 16;
+    l2norm_fwd128_kernel<<<(unsigned)(groups < cap ? groups : cap), 256, 0, st>>>(X, mask, n_tok, Y);
+  } else {
+    l2norm_fwd_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(X, mask, n_tok, d, Y);
+  }
   EVDR_LAUNCH_CHECK("l2norm_fwd_kernel");
   return EVDR_OK;
 }
@@ -396,7 +480,13 @@ int evdr_l2norm_bwd(evdr_handle* h, const float* X, const uint8_t* mask, const f
   EVDR_REQUIRE_HANDLE(h);
   EVDR_CHECK_ARG(X && gY && gX && n_tok >= 1 && d >= 4 && d % 4 == 0, "evdr_l2norm_bwd: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  l2norm_bwd_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(X, mask, gY, n_tok, d, gX);
+  if (d == 128) {
+    const long long groups = (n_tok + 8 * L2N_TPW - 1) / (8 * L2N_TPW);
+    const long long cap = (long long)h->sm_count * 16;
+    l2norm_bwd128_kernel<<<(unsigned)(groups < cap ? groups : cap), 256, 0, st>>>(X, mask, gY, n_tok, gX);
+  } else {
+    l2norm_bwd_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(X, mask, gY, n_tok, d, gX);
+  }
   EVDR_LAUNCH_CHECK("l2norm_bwd_kernel");
   return EVDR_OK;
 }

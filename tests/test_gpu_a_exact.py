@@ -105,11 +105,14 @@ def test_cpu_inputs_raise(evdr):
 
 
 # ----------------------------------------------------------------------------- fused l2 normalise
-def test_l2_normalize_masked(evdr, cuda):
+@pytest.mark.parametrize("n,l,d", [(6, 50, 128), (3, 7, 128), (2, 4, 128), (5, 9, 64), (1000, 41, 128)])
+def test_l2_normalize_masked(evdr, cuda, n, l, d):
+    """d == 128 runs the register-resident 4-tokens-per-warp kernels (incl. token counts that are not a
+    multiple of 4), other dims the generic one-warp-per-token kernels."""
     g = torch.Generator().manual_seed(9)
-    X = torch.randn(6, 50, 128, generator=g).to(cuda)
+    X = torch.randn(n, l, d, generator=g).to(cuda)
     X[1, 3] = 0
-    m = (torch.rand(6, 50, generator=g) > 0.2).to(cuda)
+    m = (torch.rand(n, l, generator=g) > 0.2).to(cuda)
     Xa = X.clone().requires_grad_(True)
     Xb = X.clone().requires_grad_(True)
     Y = evdr.l2_normalize_masked(Xa, m)
@@ -119,7 +122,7 @@ def test_l2_normalize_masked(evdr, cuda):
     gy = torch.randn(Y.shape, generator=g).to(cuda)
     Y.backward(gy)
     Yr.backward(gy)
-    sel = torch.ones(6, 50, dtype=torch.bool, device=cuda)
+    sel = torch.ones(n, l, dtype=torch.bool, device=cuda)
     sel[1, 3] = False  # zero vector: torch's norm backward is 0/0-guarded differently
     np.testing.assert_allclose(Xa.grad[sel].cpu().numpy(), Xb.grad[sel].cpu().numpy(), rtol=1e-4, atol=1e-5)
 
