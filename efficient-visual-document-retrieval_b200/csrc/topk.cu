@@ -275,12 +275,21 @@ topk_small_kernel(const float* __restrict__ scores, long long ld, int n,
     thr_s = warp_kth_largest(m, k, lane);
   }
   int filled = 0;                            // insertions so far (the list's k-th entry is real once >= k)
+  // software pipeline: the next 128 columns are in flight while the current 128 are filtered
+  float nxt[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = wbeg + u * 32 + lane;
+    nxt[u] = (i < wend) ? __ldcs(row + i) : -INFINITY;
+  }
   for (int base = wbeg; base < wend; base += 128) {
     float s[4];
 #pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = nxt[u];
+#pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = base + u * 32 + lane;
-      s[u] = (i < wend) ? row[i] : -INFINITY;
+      const int i = base + 128 + u * 32 + lane;
+      nxt[u] = (i < wend) ? __ldcs(row + i) : -INFINITY;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
