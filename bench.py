@@ -6,8 +6,9 @@
 
 A "step" is one pass of the hot path over one batch: 1024 queries (32 tokens, 128-d) scored against
 this rank's 100 000-page shard (1030 valid tokens per page, stored as 1040 bf16 slots) with the
-tcgen05 MaxSim kernel, followed by the local top-10 and -- for N > 1 -- the NCCL all-gather + merge
-of the candidates (BASELINE.json configs[2] per GPU; the corpus grows with N: weak scaling).
+tcgen05 MaxSim kernel, followed by the local top-10 and -- for N > 1 -- the exchange + merge of the
+candidates (one peer-memory kernel over NVLink by default, ncclAllGather + merge with --exchange
+nccl).  BASELINE.json configs[2] per GPU; the corpus grows with N: weak scaling.
 
 value     : whole-job pairs/s with everything resident in HBM (CUDA events, max over ranks)
 e2e       : same metric through the reference-facing call score_multi_vector_masked(Q, P, qmask,
@@ -194,7 +195,7 @@ def workload_config(args, n_gpus):
     return {
         "workload": f"query-batched MaxSim: {args.queries} queries x {args.pages} pages per GPU "
                     f"(BASELINE.json configs[2]), then top-{TOPK}"
-                    + (" + NCCL all-gather merge" if n_gpus > 1 else ""),
+                    + (" + candidate exchange over NVLink and merge" if n_gpus > 1 else ""),
         "queries": args.queries, "pages_per_gpu": args.pages, "pages_total": args.pages * n_gpus,
         "tokens_per_page": LP_VALID, "token_slots_per_page": LP_SLOTS, "query_tokens": LQ, "dim": D,
         "top_k": TOPK, "parallelism": f"page-sharded x{n_gpus}, queries replicated",
