@@ -42,7 +42,9 @@ _SIGNATURES = {
     "evdr_maxsim_packed_fwd": ([_vp, _vp, _vp, _i, _vp, _i64, _vp, _i, _i64, _i, _i, _vp, _i64, _vp], _i),
     "evdr_maxsim_packed_argmax": ([_vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp], _i),
     "evdr_maxsim_rescore": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
-    "evdr_maxsim_train_fwd": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "evdr_maxsim_train_fwd": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "evdr_maxsim_packed_argmax_scores": ([_vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp, _i64, _vp], _i),
+    "evdr_slots_to_tokens": ([_vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "evdr_group_sum": ([_vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp], _i),
     "evdr_hard_token_argmax": ([_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "evdr_topk": ([_vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp], _i),

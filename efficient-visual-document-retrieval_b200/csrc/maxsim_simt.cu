@@ -327,6 +327,25 @@ rescore_kernel(const TQ* __restrict__ Q, const TP* __restrict__ P, const uint8_t
   }
 }
 
+// Packed slot -> page-token index for every (page, query-token row): a filler slot (masked or beyond lp)
+// names the valid token it duplicates (nearest preceding valid token, else the first valid one -- the pack
+// rule); a page without valid tokens maps to 0 (it receives no gradient).
+__global__ void __launch_bounds__(256)
+slot_to_token_kernel(const uint8_t* __restrict__ pmask, int32_t* __restrict__ am, long long n, int R, int lp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* mc = pmask + (i / R) * lp;
+  int t = am[i];
+  t = t < 0 ? 0 : (t >= lp ? lp - 1 : t);
+  if (!mc[t]) {
+    int u = t;
+    while (u >= 0 && !mc[u]) --u;
+    if (u < 0) { u = 0; while (u < lp && !mc[u]) ++u; }
+    t = u < lp ? u : 0;
+  }
+  am[i] = t;
+}
+
 // any d % 4 == 0: one warp per (query-token row, page)
 template <typename TQ, typename TP>
 __global__ void __launch_bounds__(256)
@@ -515,6 +534,17 @@ int evdr_hard_token_argmax(evdr_handle* h, const void* Q, int q_dtype, const voi
   else return set_error(EVDR_ERR_INVALID, "evdr_hard_token_argmax: dtype must be EVDR_F32 or EVDR_BF16");
 #undef EVDR_HT
   EVDR_LAUNCH_CHECK("hard_token_kernel");
+  return EVDR_OK;
+}
+
+int evdr_slots_to_tokens(evdr_handle* h, const uint8_t* pmask, int32_t* argmax, int np, int n_rows, int lp,
+                         void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(pmask && argmax && np >= 1 && n_rows >= 1 && lp >= 1, "evdr_slots_to_tokens: bad arguments");
+  const long long n = (long long)np * n_rows;
+  slot_to_token_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(pmask, argmax, n,
+                                                                                                n_rows, lp);
+  EVDR_LAUNCH_CHECK("slot_to_token_kernel");
   return EVDR_OK;
 }
 

@@ -451,6 +451,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                 const int slot = (bc - pstart) * EVDR_CHUNK + bp;
                 if (qidx[r] >= 0 && lane < prm.lq)
                   prm.argmax[(size_t)p * ((size_t)prm.nq * prm.lq) + (size_t)qidx[r] * prm.lq + lane] = slot;
+                if (prm.out != nullptr) {                 // scores too (gradient calls: search + score in one pass)
+                  const float sc = warp_sum(rm * qm[r]);
+                  if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = sc;
+                }
                 pstart = pe;
                 bc = pe;
               } else {
@@ -775,6 +779,20 @@ extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint
   if (!out) return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed_fwd: out is null");
   return packed_dispatch(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks,
                          pages_per_item, out, out_ld, nullptr, EVDR_TC_LQ, k_blocks, stream);
+}
+
+extern "C" int evdr_maxsim_packed_argmax_scores(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,
+                                                int lq, const void* tokens, int64_t n_tokens,
+                                                const int32_t* chunk_off, int np, int64_t total_chunks,
+                                                int k_blocks, int32_t* argmax_slots, float* out, int64_t out_ld,
+                                                void* stream) {
+  if (!argmax_slots || !out)
+    return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed_argmax_scores: null output pointer");
+  if (lq < 1 || lq > EVDR_TC_LQ)
+    return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed_argmax_scores: lq=%d outside [1,32]", lq);
+  if (out_ld < np) return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed_argmax_scores: out_ld < np");
+  return packed_dispatch(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, 0, out, out_ld,
+                         argmax_slots, lq, k_blocks, stream);
 }
 
 extern "C" int evdr_maxsim_packed_argmax(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,

@@ -119,10 +119,11 @@ def _backward_through_argmax(ctx, g):
 
 
 class _MaxSimRescoreFn(torch.autograd.Function):
-    """Gradient calls on ColPali shapes: tcgen05 search for the winning page token of every
-    (query token, page) on bf16 operands, then exact fp32 rescoring of the winners on the original
-    operands (evdr_maxsim_packed_argmax + evdr_maxsim_rescore); the backward scatters through the same
-    indices.  Equal to the exact path wherever bf16 and fp32 pick the same token."""
+    """Gradient calls on ColPali shapes: ONE tcgen05 pass on bf16x3-split operands gives the scores (to
+    ~5e-6 relative of the fp32 values) and the winning page token of every (query token, page); the
+    backward scatters through those indices.  EVDR_TRAIN_RESCORE=1 recomputes the winners' dot products
+    exactly in fp32 on the original operands instead (evdr_maxsim_rescore), as does the composed path for
+    problems beyond one call."""
 
     @staticmethod
     def forward(ctx, Q, P, qm, pm):
@@ -137,9 +138,10 @@ class _MaxSimRescoreFn(torch.autograd.Function):
             # one library call (evdr_maxsim_train_fwd): both packs, the search, the rescoring and the sum
             am = torch.empty((npg, R), dtype=torch.int32, device=dev)
             out = torch.empty((nq, npg), dtype=torch.float32, device=dev)
+            rescore = 1 if os.environ.get("EVDR_TRAIN_RESCORE", "0") == "1" else 0
             _lib.check(lib.evdr_maxsim_train_fwd(h, Q.data_ptr(), _lib.dtype_code(Q), P.data_ptr(), _lib.dtype_code(P),
-                                                 qm.data_ptr(), pm.data_ptr(), nq, npg, lq, lp, d, am.data_ptr(),
-                                                 out.data_ptr(), st), "evdr_maxsim_train_fwd")
+                                                 qm.data_ptr(), pm.data_ptr(), nq, npg, lq, lp, d, rescore,
+                                                 am.data_ptr(), out.data_ptr(), st), "evdr_maxsim_train_fwd")
             ctx.save_for_backward(Q, P, qm, pm, am)
             return out
         # larger problems: the same steps composed here, the rescoring in page blocks

@@ -188,15 +188,27 @@ EVDR_API int evdr_maxsim_rescore(evdr_handle* h,
                                  float* rowmax_ws_dev, float* out_dev, void* stream);
 
 /* The forward of a gradient call in ONE library call: evdr_pack_queries(k_blocks=3) + evdr_pack_plan +
- * evdr_pack_pages(k_blocks=3) + evdr_maxsim_packed_argmax + evdr_maxsim_rescore on a stream-ordered
- * workspace (the student tensor changes every step, mainv2_iter_listwise.py:280,287, so nothing can be
+ * evdr_pack_pages(k_blocks=3) + one tcgen05 pass on a stream-ordered
+ * workspace.  rescore == 0: the pass yields scores AND winners (bf16x3 contraction: <Q,P> to ~2^-18
+ * relative, measured <= 5e-6 on the scores); rescore != 0: winners only, their dot products are recomputed
+ * exactly in fp32 on the original operands (evdr_maxsim_rescore) (the student tensor changes every step, mainv2_iter_listwise.py:280,287, so nothing can be
  * cached and the host-side issue time is paid per step).  Q (nq, lq, 128) with lq <= 32 or lq in
  * {64, 96, 128} (zero-padded, masked); argmax_dev int32 [np, nq*lq] receives the winning page-token
  * indices for evdr_maxsim_bwd; out_dev fp32 [nq, np]. */
 EVDR_API int evdr_maxsim_train_fwd(evdr_handle* h, const void* Q_dev, int q_dtype, const void* P_dev,
                                    int p_dtype, const uint8_t* qmask_dev, const uint8_t* pmask_dev,
-                                   int nq, int np, int lq, int lp, int d, int32_t* argmax_dev,
+                                   int nq, int np, int lq, int lp, int d, int rescore, int32_t* argmax_dev,
                                    float* out_dev, void* stream);
+/* The pieces of the rescore == 0 route: evdr_maxsim_packed_argmax_scores is evdr_maxsim_packed_argmax that
+ * ALSO writes the scores of the same pass (out_dev fp32 [nq, out_ld]); evdr_slots_to_tokens turns packed slots
+ * into page-token indices in place (fillers -> the valid token they duplicate; empty pages -> 0). */
+EVDR_API int evdr_maxsim_packed_argmax_scores(evdr_handle* h, const void* Qb_dev, const uint8_t* qmask32_dev,
+                                              int nq, int lq, const void* tokens_dev, int64_t n_tokens,
+                                              const int32_t* chunk_off_dev, int np, int64_t total_chunks,
+                                              int k_blocks, int32_t* argmax_slots_dev, float* out_dev,
+                                              int64_t out_ld, void* stream);
+EVDR_API int evdr_slots_to_tokens(evdr_handle* h, const uint8_t* pmask_dev, int32_t* argmax_dev, int np,
+                                  int n_rows, int lp, void* stream);
 
 /* A8  hard-token mining (mainv3_iter_liscore_QA_hardtoken.py:398-425): for every (query q, page
  * doc_idx[q, a]) the index of the VALID page token m maximising max_{valid n} <Q[q,n], P[c,m]> (the

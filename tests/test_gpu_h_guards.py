@@ -67,8 +67,9 @@ def test_topk_outputs_stay_inside_their_block(evdr, cuda, nq, n, k):
     assert torch.equal(flat_v[32:32 + nq * k].view(nq, k)[:, : min(k, n)], want)
 
 
+@pytest.mark.parametrize("rescore", [0, 1])
 @pytest.mark.parametrize("nq,npg,ls,lq", [(32, 100, 41, 32), (5, 33, 206, 32), (9, 64, 21, 64), (1, 7, 1, 1)])
-def test_training_forward_and_backward_stay_inside_their_buffers(evdr, cuda, nq, npg, ls, lq):
+def test_training_forward_and_backward_stay_inside_their_buffers(evdr, cuda, nq, npg, ls, lq, rescore):
     lib = evdr._lib.load()
     h = evdr._lib.handle(cuda)
     st = evdr._lib.stream_ptr(cuda)
@@ -82,7 +83,7 @@ def test_training_forward_and_backward_stay_inside_their_buffers(evdr, cuda, nq,
     am = torch.full((npg * R + 2 * pad,), SENT_I, dtype=torch.int32, device=cuda)
     out = torch.full((nq * npg + 2 * pad,), SENT_F, dtype=torch.float32, device=cuda)
     evdr._lib.check(lib.evdr_maxsim_train_fwd(h, Q.data_ptr(), 0, P.data_ptr(), 0, qm.data_ptr(), pm.data_ptr(), nq, npg,
-                                              lq, ls, 128, am[pad:].data_ptr(), out[pad:].data_ptr(), st),
+                                              lq, ls, 128, rescore, am[pad:].data_ptr(), out[pad:].data_ptr(), st),
                     "evdr_maxsim_train_fwd")
     for buf, sent, n in ((am, SENT_I, npg * R), (out, SENT_F, nq * npg)):
         assert bool((buf[:pad] == sent).all() and (buf[pad + n:] == sent).all()), "guard overwritten"
