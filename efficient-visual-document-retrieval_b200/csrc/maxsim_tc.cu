@@ -737,8 +737,21 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
       if (ppi > p32k) ppi = p32k < 1 ? 1 : p32k;
     }
     if (ppi >= 16) ppi = (ppi / 16) * 16;
-    // ... and there must be enough items to balance the grid
-    while (ppi > 1 && (long long)((np + ppi - 1) / ppi) * n_qgroups < 16LL * units) ppi = (ppi + 1) / 2;
+    // ... and there must be enough items to balance the grid -- but every item change reloads the query
+    // tiles (~2 us, about 3.5 tile passes, with the tensor pipe idle), which dominates SMALL problems when items
+    // shrink to a page or two (a 32 x 1000-page teacher call ran 12-pass items: 25 % reload time).  With
+    // P passes per CTA in total, items of p passes lose ~3.5/p to reloads and ~p/(2P) to the tail: the optimum
+    // is p = sqrt(7 P).  Items stay within the caps above and never fewer than one per CTA.
+    {
+      const int bn = (k_blocks == 3) ? 64 : (want_ta ? 192 : 256);
+      const double avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
+      const double passes_per_cta = (double)total_chunks * EVDR_CHUNK / bn * prm.nqt / (double)units;
+      const double item_passes = sqrt(7.0 * passes_per_cta);
+      int ppi_bal = (int)(item_passes * bn / (avg_tok * tpg) + 0.5);
+      if (ppi_bal < 1) ppi_bal = 1;
+      if (ppi > ppi_bal) ppi = ppi_bal;
+      while (ppi > 1 && (long long)((np + ppi - 1) / ppi) * n_qgroups < (long long)units) ppi = (ppi + 1) / 2;
+    }
   }
   if (ppi > np) ppi = np;
   prm.ppi = ppi;
