@@ -473,10 +473,11 @@ class CustomRetrievalEvaluator:
             m[4] = retrieval_metrics(ids2, qrel_off, qrel_ids, qrel_rels, self.k_values)[4]
         return self._format(m.cpu())
 
-    def _format(self, m: torch.Tensor) -> Dict[str, Dict[str, float]]:
-        def mean(row):  # Python float sum like mteb (sum(list)/len)
+    def _format(self, m: torch.Tensor, mrr_den: Optional[int] = None) -> Dict[str, Dict[str, float]]:
+        def mean(row, den=None):  # Python float sum like mteb (sum(list)/len)
             vals = row.tolist()
-            return round(sum(vals) / len(vals), 5) if vals else 0.0
+            den = len(vals) if den is None else den
+            return round(sum(vals) / den, 5) if vals and den else 0.0
 
         ks = self.k_values
         return {
@@ -484,7 +485,8 @@ class CustomRetrievalEvaluator:
             "mAP": {f"MAP@{k}": mean(m[1, j]) for j, k in enumerate(ks)},
             "Recall": {f"Recall@{k}": mean(m[2, j]) for j, k in enumerate(ks)},
             "Precision": {f"P@{k}": mean(m[3, j]) for j, k in enumerate(ks)},
-            "mRR": {f"MRR@{k}": mean(m[4, j]) for j, k in enumerate(ks)},
+            # mteb's mrr divides by len(qrels): judged queries without results count as 0
+            "mRR": {f"MRR@{k}": mean(m[4, j], mrr_den) for j, k in enumerate(ks)},
         }
 
     # reference signature ------------------------------------------------------------------------
@@ -544,4 +546,4 @@ class CustomRetrievalEvaluator:
         rels_t = torch.tensor(rels, dtype=torch.int32)
         m = retrieval_metrics(i1, off_t, ids_t, rels_t, self.k_values)
         m[4] = retrieval_metrics(i2, off_t, ids_t, rels_t, self.k_values)[4]
-        return self._format(m.cpu())
+        return self._format(m.cpu(), mrr_den=len(relevant_docs))

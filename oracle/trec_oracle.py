@@ -17,7 +17,7 @@ Third-party code restated here (absent from /root/reference, unpinned there):
   results are scored; each measure is averaged over scored queries and rounded to
   5 decimals.  ``evaluate_custom(..., "mrr")``: per query sort (stable, Python
   ``sorted(..., reverse=True)``) by score, take top k_max, reciprocal rank of the
-  first doc with rel>0 within top-k; mean, round 5.
+  first doc with rel>0 within top-k; sum / len(qrels), round 5.
 """
 from __future__ import annotations
 
@@ -89,7 +89,10 @@ def mrr(relevant_docs, results, k_values=K_VALUES):
                 if d in rel:
                     tot[k] += 1.0 / (rank + 1)
                     break
-    n = max(len(results), 1)
+    # BEIR / mteb 1.x divide by len(qrels) -- every judged query counts, scored or not (the other measures
+    # average over the scored queries only); identical whenever every judged query has results, as in the
+    # reference's scripts
+    n = max(len(relevant_docs), 1)
     return {f"MRR@{k}": round(tot[k] / n, 5) for k in k_values}
 
 
