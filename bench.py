@@ -378,7 +378,7 @@ def main():
                                      ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and n_gpus == 1:      # reported on rank 0 at N = 1 only
             try:
                 cpu, _ = cpu_reference_rate()
             except Exception as e:
