@@ -111,7 +111,7 @@ class ClockSampler:
             self.proc.wait(2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, pw, mx, reasons = [], [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -122,63 +122,73 @@ class ClockSampler:
                 mx = float(f[2])
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for nm, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "sm_mhz_min": min(sm) if sm else None, "power_w": statistics.median(pw) if pw else None,
                 "reasons": sorted(reasons)}
 
 
-# --------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_rate(seconds_target: float = 12.0, n_queries: int = 32):
-    """Reference algorithm (oracle port of evaluator/retrieval.py:166-213, torch CPU, fp32, chunk_p=64)
-    on a bounded sample of the workload: n_queries x S pages of 1030 tokens."""
-    import torch
+# --------------------------------------------------------------------------------------- baselines
+# The reference arm / cpu_baseline score a FIXED bounded sample of the workload (per-pair cost is
+# size-independent): REF_Q queries x REF_P pages of 1030 tokens, fp32, chunk_p = 64.
+REF_Q, REF_P, REF_CHUNK = 32, 2048, 64
+REF_SAMPLE = (f"{REF_Q} queries x {REF_P} pages x {LP_VALID} tokens fp32, chunk_p={REF_CHUNK} "
+              f"(bounded sample of the workload; per-pair cost is size-independent)")
+
+
+def reference_scorer():
+    """(fn, kind): the reference's own score_multi_vector_masked, executed UNMODIFIED from baseline/_ref
+    (tools/stage_reference.py; sha256-checked) -> kind "reference"; only if that tree is absent, the
+    oracle's torch-CPU restatement of the same loop -> kind "port"."""
+    from baseline import ref
+    if ref.available():
+        return ref.scorer_module().score_multi_vector_masked, "reference"
     from oracle.maxsim_oracle import maxsim_masked_torch_cpu
+    return maxsim_masked_torch_cpu, "port"
+
+
+def reference_sample(device="cpu"):
+    import torch
+    g = torch.Generator().manual_seed(42)
+    P = torch.nn.functional.normalize(torch.randn(REF_P, LP_VALID, D, generator=g), dim=-1).to(device)
+    Q = torch.nn.functional.normalize(torch.randn(REF_Q, LQ, D, generator=g), dim=-1).to(device)
+    return (Q, P, torch.ones(REF_Q, LQ, dtype=torch.bool, device=device),
+            torch.ones(REF_P, LP_VALID, dtype=torch.bool, device=device))
+
+
+def cpu_reference_rate(steps: int = 3, warmup: int = 1):
+    """The reference's CPU path on the box's host cores: `steps` timed passes over the fixed sample."""
+    import torch
+    fn, kind = reference_scorer()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g = torch.Generator().manual_seed(42)
-    def sample(n_pages):
-        P = torch.nn.functional.normalize(torch.randn(n_pages, LP_VALID, D, generator=g), dim=-1)
-        Q = torch.nn.functional.normalize(torch.randn(n_queries, LQ, D, generator=g), dim=-1)
-        return Q, P, torch.ones(n_queries, LQ, dtype=torch.bool), torch.ones(n_pages, LP_VALID, dtype=torch.bool)
-    Q, P, qm, pm = sample(64)
-    maxsim_masked_torch_cpu(Q, P, qm, pm, 64)                      # warm-up
-    t0 = time.perf_counter()
-    maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
-    rate = n_queries * 64 / (time.perf_counter() - t0)
-    n_pages = int(max(64, min(4096, (rate * seconds_target / n_queries) // 64 * 64)))
-    Q, P, qm, pm = sample(n_pages)
-    # at least `seconds_target` of CPU work: the page sample is capped at 4096 pages (2.2 GB fp32), faster
-    # hosts repeat the same pass
-    reps, dt = 0, 0.0
-    while reps == 0 or (dt < seconds_target and reps < 64):
+    Q, P, qm, pm = reference_sample()
+    with torch.no_grad():
+        for _ in range(warmup):
+            fn(Q, P[:256], qm, pm[:256], REF_CHUNK)
         t0 = time.perf_counter()
-        maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
-        dt += time.perf_counter() - t0
-        reps += 1
-    return {"value": reps * n_queries * n_pages / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{reps} pass(es) of {n_queries} queries x {n_pages} pages x {LP_VALID} tokens fp32, chunk_p=64, "
-                      f"{dt:.2f} s in total"}, (Q, P, qm, pm)
+        for _ in range(steps):
+            fn(Q, P, qm, pm, REF_CHUNK)
+        dt = (time.perf_counter() - t0) / max(1, steps)
+    return {"value": REF_Q * REF_P / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{steps} pass(es) of {REF_SAMPLE}, {dt:.2f} s per pass",
+            "function": "evaluator/retrieval.py:166-213 score_multi_vector_masked"
+                        + (" (unmodified, baseline/_ref)" if kind == "reference" else " (oracle port)")}, dt
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port -- the
-    reference is pure Python and /root/reference does not exist on the GPU box) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, all threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from oracle.maxsim_oracle import maxsim_masked_torch_cpu
-    base, (Q, P, qm, pm) = cpu_reference_rate(seconds_target=max(2.0, 40.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        maxsim_masked_torch_cpu(Q, P, qm, pm, 64)
-    dt = (time.perf_counter() - t0) / max(1, args.steps)
-    value = Q.shape[0] * P.shape[0] / dt
-    base["value"] = value
+    base, dt = cpu_reference_rate(steps=max(1, args.steps), warmup=1 if args.warmup else 0)
+    value = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -191,6 +201,44 @@ def run_reference_arm(args):
     emit(line)
 
 
+def gpu_reference_rate(torch, dev, timed):
+    """The SAME unmodified reference function, torch-eager on this B200 (that is the bar a
+    CUDA user of the reference has today).  Config 1 in full (500 x 500 x 1030, queries batched by 64 to
+    bound the (Q, C, Lq, Lp) intermediate; outputs are batch-invariant) and the reference-arm sample of
+    configs[2]; CUDA events, synchronised on both sides."""
+    fn, kind = reference_scorer()
+    out = {"kind": kind, "function": "evaluator/retrieval.py:166-213 score_multi_vector_masked, torch eager fp32 on the GPU"}
+    g = torch.Generator().manual_seed(7)
+    P = torch.nn.functional.normalize(torch.randn(500, LP_VALID, D, generator=g), dim=-1).to(dev)
+    Q = torch.nn.functional.normalize(torch.randn(500, LQ, D, generator=g), dim=-1).to(dev)
+    qm = torch.ones(500, LQ, dtype=torch.bool, device=dev)
+    pm = torch.ones(500, LP_VALID, dtype=torch.bool, device=dev)
+
+    def config1():
+        with torch.no_grad():
+            return torch.cat([fn(Q[i:i + 64], P, qm[i:i + 64], pm, REF_CHUNK) for i in range(0, 500, 64)])
+
+    ms = timed(config1, 3, 1)
+    out["config1_500x500"] = {"ms": ms, "pairs_per_s": 500 * 500 / (ms * 1e-3)}
+    import evdr_b200 as evdr
+    ours = lambda: evdr.score_multi_vector_masked(Q, P, qm, pm, REF_CHUNK)
+    ms_o = timed(ours, 10, 3)
+    ref_s, our_s = config1(), ours()
+    out["config1_500x500"]["ours_ms"] = ms_o
+    out["config1_500x500"]["ours_pairs_per_s"] = 500 * 500 / (ms_o * 1e-3)
+    out["config1_500x500"]["max_rel_diff"] = float(((ref_s - our_s).abs() / ref_s.abs().clamp_min(1)).max())
+    del P, Q, qm, pm, ref_s, our_s
+    Qs, Ps, qms, pms = reference_sample(dev)
+
+    def sample():
+        with torch.no_grad():
+            return fn(Qs, Ps, qms, pms, REF_CHUNK)
+
+    ms = timed(sample, 3, 1)
+    out["configs2_sample"] = {"ms": ms, "pairs_per_s": REF_Q * REF_P / (ms * 1e-3), "sample": REF_SAMPLE}
+    return out
+
+
 def workload_config(args, n_gpus):
     return {
         "workload": f"query-batched MaxSim: {args.queries} queries x {args.pages} pages per GPU "
@@ -200,8 +248,10 @@ def workload_config(args, n_gpus):
         "tokens_per_page": LP_VALID, "token_slots_per_page": LP_SLOTS, "query_tokens": LQ, "dim": D,
         "top_k": TOPK, "parallelism": f"page-sharded x{n_gpus}, queries replicated",
         "exchange": "none (1 GPU)" if n_gpus == 1 else
-                    ("ncclAllGather + merge" if args.exchange == "nccl" else "one-kernel peer-memory exchange + merge"),
+                    ("ncclAllGather + merge (headline); one-kernel peer-memory exchange timed beside it"
+                     if args.exchange == "nccl" else "one-kernel peer-memory exchange + merge"),
         "l2": f"inputs larger than L2 ({args.pages * LP_SLOTS * D * 2 / 1e9:.1f} GB corpus per GPU vs 126 MB)",
+        "reference_arm_sample": REF_SAMPLE,
     }
 
 
@@ -216,9 +266,10 @@ def main():
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--no-extras", action="store_true", help="skip the single-query / 64-query side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
-                    help="candidate exchange at N > 1: ncclAllGather + merge, or the one-kernel peer-memory exchange")
-    ap.add_argument("--corpus-1m", action="store_true", help="also run the 1M-page top-10 QPS measurement at 2 GPUs")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="candidate exchange of the headline at N > 1: ncclAllGather + merge (north_star) or the "
+                         "one-kernel peer-memory exchange; the other mode is timed beside it")
+    ap.add_argument("--no-corpus-1m", action="store_true", help="skip the 1M-page (N >= 2) / 500k-page (N = 1) top-10 QPS runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -243,18 +294,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    peer_ok = False
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         evdr.init_nccl_comm(dev)
-        if args.exchange == "peer":
-            # init_peer_exchange either succeeds on every rank or raises on every rank (CUDA IPC peer
-            # access unavailable somewhere): then all ranks use the NCCL exchange
-            try:
-                evdr.init_peer_exchange(dev, max_candidates=max(args.queries, 64) * TOPK)
-            except Exception as e:
-                print(f"[bench] peer exchange unavailable on rank {rank}: {e!r}; using NCCL", file=sys.stderr)
-                args.exchange = "nccl"
+        # the peer-memory exchange is set up whenever the box allows it, so that both modes are timed;
+        # init_peer_exchange either succeeds on every rank or raises on every rank
+        try:
+            evdr.init_peer_exchange(dev, max_candidates=max(args.queries, 64) * TOPK)
+            peer_ok = True
+        except Exception as e:
+            print(f"[bench] peer exchange unavailable on rank {rank}: {e!r}; using NCCL", file=sys.stderr)
+            args.exchange = "nccl"
     n_gpus = world
     xmode = args.exchange if world > 1 else "nccl"
     peaks = load_peaks()
@@ -272,10 +324,15 @@ def main():
     qm = qmh.to(dev)
     scores = torch.empty((nq, npg), dtype=torch.float32, device=dev)
     search = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode=xmode)
+    kernel_events = []                                                # (start, end) around the dominant kernel
 
-    def step():
+    def step(search=search):
         Qb, qm32 = evdr.pack_queries(Q, qm)                          # 1 launch  (pack_queries_kernel)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()                                                  # torch's current stream IS the launch stream
         pk.score_packed(Qb, qm32, out=scores)                        # 1 launch  (maxsim_tc_kernel)
+        e1.record()
+        kernel_events.append((e0, e1))
         return search.topk(scores, TOPK)                             # 1 launch  (topk_select_kernel); N > 1:
                                                                      # + unpack_gathered + merge (+ NCCL's own)
     launches_per_step = 3 if n_gpus == 1 else (4 if xmode == "peer" else 5)
@@ -309,6 +366,26 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     pairs_per_step = nq * npg * n_gpus
     value = pairs_per_step / (ms_step * 1e-3)
+    # the dominant kernel's share of those very steps (CUDA events on its launch stream, warm-up excluded)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kernel_events[-args.steps:]) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_kernel], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_kernel = float(t.item())
+
+    # ---- N > 1: the merged result is checked, and the other exchange mode is timed on the same steps
+    sharded_check, exchange_modes = None, None
+    if world > 1:
+        sharded_check = check_sharded_result(torch, dist, step(), scores, npg, rank, world, dev)
+        exchange_modes = {xmode: {"ms_per_step": ms_step, "value": value}}
+        other = "peer" if xmode == "nccl" else "nccl"
+        if other == "nccl" or peer_ok:
+            s2 = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode=other)
+            ms2 = timed(lambda: step(s2), args.steps, 1)
+            exchange_modes[other] = {"ms_per_step": ms2, "value": pairs_per_step / (ms2 * 1e-3)}
+            chk2 = check_sharded_result(torch, dist, step(s2), scores, npg, rank, world, dev)
+            if chk2 != "ok":
+                sharded_check = f"{other}: {chk2}"
 
     # ---- end to end through the reference-facing call, host buffers in the timed region
     host_scores = torch.empty((nq, npg), dtype=torch.float32).pin_memory()
@@ -324,11 +401,10 @@ def main():
            "h2d_bytes_per_step": Qh.numel() * 4 + qmh.numel(), "d2h_bytes_per_step": host_scores.numel() * 4,
            "call": "score_multi_vector_masked(Q, P, qmask, pmask, 64); page tensor resident on the device "
                    "as in the reference (mainv2_iter_listwise.py:96), queries from pinned host memory, "
-                   "full (nq, np) score matrix read back"}
+                   "full (nq, np) score matrix read back; the zero-copy packed view of the frozen page tensor "
+                   "comes from the pack cache (built once, on the first warm-up call)"}
 
-    # ---- roofline of the dominant kernel, timed alone on its launch stream
-    Qb, qm32 = evdr.pack_queries(Q, qm)
-    ms_kernel = timed(lambda: pk.score_packed(Qb, qm32, out=scores), args.steps, 1)
+    # ---- roofline of the dominant kernel: its CUDA-event time INSIDE the timed steps above
     flops = nq * npg * FLOPS_PER_PAIR
     achieved = flops / (ms_kernel * 1e-3) / 1e12
     # denominator: the measured BURST cuBLAS bf16 peak (the higher of the two measured figures, so the
@@ -340,7 +416,8 @@ def main():
                 "peak_kind": f"{peaks['source']} burst cuBLAS bf16 (8192^3, best of 10)",
                 "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
                 "sustained_peak": peaks["bf16_tflops_sustained"],
-                "ms_per_launch": ms_kernel, "algorithmic_flops_per_launch": flops,
+                "ms_per_launch": ms_kernel, "timed": "CUDA events around the kernel inside the timed steps",
+                "share_of_step": ms_kernel / ms_step, "algorithmic_flops_per_launch": flops,
                 "algorithmic_bytes_per_launch": npg * BYTES_PER_PAGE, "traffic": measured_traffic(nq, npg)}
 
     extras = {}
@@ -360,18 +437,26 @@ def main():
         # candidate exchange alone (local top-10 + exchange + merge of resident scores), both modes
         if n_gpus > 1:
             try:
-                extras["exchange_us"] = exchange_latency(evdr, torch, dev, rank, npg, timed, xmode)
+                extras["exchange_us"] = exchange_latency(evdr, torch, dev, rank, npg, timed, peer_ok)
             except Exception as e:
                 extras["exchange_us"] = {"error": repr(e)}
-        # BASELINE.json configs[3]: top-10 QPS on a 1 M-page corpus sharded over the box (needs the
-        # memory of >= 4 GPUs at 100k pages already resident; 2 GPUs only with --corpus-1m)
-        if n_gpus >= 4 or (n_gpus >= 2 and args.corpus_1m):
+        # the unmodified reference function torch-eager on this B200 (N = 1, rank 0)
+        if n_gpus == 1:
+            try:
+                extras["gpu_reference"] = gpu_reference_rate(torch, dev, timed)
+            except Exception as e:
+                extras["gpu_reference"] = {"error": repr(e)}
+        # BASELINE.json configs[3]: top-10 QPS on a 1 M-page corpus sharded over the box (N >= 2: 500 k pages =
+        # 133 GB per GPU at N = 2); the 1-GPU point is a 500 k-page corpus
+        if not args.no_corpus_1m:
             try:
                 del pk, corpus, pmask, scores, host_scores
                 torch.cuda.empty_cache()
-                extras["corpus_1m"] = corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed, xmode)
+                extras["corpus_1m" if n_gpus > 1 else "corpus_500k"] = corpus_1m(
+                    evdr, torch, dist, dev, rank, n_gpus, peaks, timed, xmode, peer_ok,
+                    total=1_000_000 if n_gpus > 1 else 500_000)
             except Exception as e:
-                extras["corpus_1m"] = {"error": repr(e)}
+                extras["corpus_1m" if n_gpus > 1 else "corpus_500k"] = {"error": repr(e)}
 
     if isinstance(extras.get("e2e_host_corpus"), dict) and "value" in extras["e2e_host_corpus"]:
         e2e["all_inputs_on_host"] = {k: extras["e2e_host_corpus"][k] for k in
@@ -392,66 +477,106 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
             "peaks": peaks,
         }
+        if n_gpus > 1:
+            line["sharded_check"] = sharded_check
+            line["exchange_modes"] = exchange_modes
+        if isinstance(extras.get("gpu_reference"), dict):
+            line["gpu_reference"] = extras.pop("gpu_reference")
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def corpus_1m(evdr, torch, dev, rank, n_gpus, peaks, timed, xmode="nccl"):
-    """Top-10 QPS on a 1,000,000-page corpus (266 GB bf16) sharded by page range over the GPUs of the
-    box: streaming single-query and 64-query batches, local scan + top-10, NCCL all-gather, merge."""
-    total = 1_000_000
+def check_sharded_result(torch, dist, merged, local_scores, npg, rank, world, dev, probes=4):
+    """Correctness of the exchange + merge at N > 1: for `probes` queries the merged top-10 must be identical
+    on every rank and equal torch.topk over the all-gathered score rows (ties: equal scores suffice)."""
+    ts, ti = merged
+    nq = local_scores.shape[0]
+    rows = sorted({0, nq // 3, (2 * nq) // 3, nq - 1})[:probes]
+    idx = torch.tensor(rows, device=dev)
+    mine = local_scores.index_select(0, idx).contiguous()
+    blocks = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(blocks, mine)
+    full = torch.cat(blocks, dim=1)                                  # global page id = rank * npg + local id
+    ref_s, ref_i = torch.topk(full, ts.shape[1], dim=1)
+    got_s, got_i = ts.index_select(0, idx), ti.index_select(0, idx)
+    if not torch.equal(got_s, ref_s):
+        return f"rank {rank}: merged top-k scores differ from torch.topk of the gathered rows"
+    tie_free = (ref_s[:, 1:] != ref_s[:, :-1]).all()
+    if bool(tie_free) and not torch.equal(got_i, ref_i):
+        return f"rank {rank}: merged top-k ids differ from torch.topk of the gathered rows"
+    if not torch.equal(full.gather(1, got_i), got_s):
+        return f"rank {rank}: merged ids do not address the merged scores"
+    all_i = [torch.empty_like(got_i) for _ in range(world)]
+    dist.all_gather(all_i, got_i.contiguous())
+    if not all(torch.equal(a, all_i[0]) for a in all_i):
+        return f"rank {rank}: ranks disagree on the merged top-k"
+    return "ok"
+
+
+def corpus_1m(evdr, torch, dist, dev, rank, n_gpus, peaks, timed, xmode="nccl", peer_ok=False, total=1_000_000):
+    """Top-10 QPS on a `total`-page corpus (1 M pages = 266 GB bf16) sharded by page range over the GPUs of the
+    box: streaming single-query and 64-query batches; local scan + top-10, candidate exchange, merge -- both
+    exchange modes when the peer regions are set up, and the merged result checked (check_sharded_result)."""
     lo, hi = evdr.partition_pages(total, n_gpus)[rank]
     npg = hi - lo
     corpus = evdr.synth.make_uniform_corpus(npg, LP_SLOTS, device=dev, seed=4242 + 1000 * rank)
     pk = evdr.PackedPages.from_uniform_tokens(corpus, page_offset=lo)
-    search = evdr.ShardedSearch((lo, hi), mode=xmode)
+    modes = [xmode] + ([m for m in ("nccl", "peer") if m != xmode and (m == "nccl" or peer_ok)] if n_gpus > 1 else [])
     out = {"exchange": xmode, "pages_total": total, "pages_per_gpu": npg, "corpus_gb_per_gpu": npg * LP_SLOTS * D * 2 / 1e9}
     for nq in (1, 64):
         g = torch.Generator().manual_seed(70 + nq)
         Q = torch.nn.functional.normalize(torch.randn(nq, LQ, D, generator=g), dim=-1).to(dev)
         qm = torch.ones((nq, LQ), dtype=torch.bool, device=dev)
         s = torch.empty((nq, npg), dtype=torch.float32, device=dev)
-
-        def one():
-            Qb, qm32 = evdr.pack_queries(Q, qm)
-            return search.topk(pk.score_packed(Qb, qm32, out=s), TOPK)
-
-        ms = timed(one, 10, 3)
-        # end to end: the query batch starts in pinned host memory, the top-10 (scores, ids) end there
         Qh, qmh = Q.cpu().pin_memory(), qm.cpu().pin_memory()
         hs = torch.empty((nq, TOPK), dtype=torch.float32).pin_memory()
         hi_ = torch.empty((nq, TOPK), dtype=torch.int64).pin_memory()
+        rec = {}
+        for mode in modes:
+            search = evdr.ShardedSearch((lo, hi), mode=mode)
 
-        def one_e2e():
-            Qb, qm32 = evdr.pack_queries(Qh.to(dev, non_blocking=True), qmh.to(dev, non_blocking=True))
-            ts, ti = search.topk(pk.score_packed(Qb, qm32, out=s), TOPK)
-            hs.copy_(ts, non_blocking=True)
-            hi_.copy_(ti, non_blocking=True)
+            def one():
+                Qb, qm32 = evdr.pack_queries(Q, qm)
+                return search.topk(pk.score_packed(Qb, qm32, out=s), TOPK)
 
-        ms_e2e = timed(one_e2e, 10, 3)
-        rec = {"ms_per_batch": ms, "top10_qps": nq / (ms * 1e-3), "pairs_per_s": nq * total / (ms * 1e-3),
-               "ms_per_batch_e2e": ms_e2e, "top10_qps_e2e": nq / (ms_e2e * 1e-3)}
-        if nq == 1:
-            gbs = npg * BYTES_PER_PAGE / (ms * 1e-3) / 1e9
-            rec["hbm_gbs_per_gpu"] = gbs
-            rec["frac_of_hbm_peak"] = gbs / peaks["hbm_gbs"]
-        else:
-            tf = nq * npg * FLOPS_PER_PAIR / (ms * 1e-3) / 1e12
-            rec["tflops_per_gpu"] = tf
-            rec["frac_of_bf16_burst_peak"] = tf / peaks["bf16_tflops"]
+            # end to end: the query batch starts in pinned host memory, the top-10 (scores, ids) end there
+            def one_e2e():
+                Qb, qm32 = evdr.pack_queries(Qh.to(dev, non_blocking=True), qmh.to(dev, non_blocking=True))
+                ts, ti = search.topk(pk.score_packed(Qb, qm32, out=s), TOPK)
+                hs.copy_(ts, non_blocking=True)
+                hi_.copy_(ti, non_blocking=True)
+
+            ms = timed(one, 10, 3)
+            ms_e2e = timed(one_e2e, 10, 3)
+            r = {"ms_per_batch": ms, "top10_qps": nq / (ms * 1e-3), "pairs_per_s": nq * total / (ms * 1e-3),
+                 "ms_per_batch_e2e": ms_e2e, "top10_qps_e2e": nq / (ms_e2e * 1e-3)}
+            if nq == 1:
+                gbs = npg * BYTES_PER_PAGE / (ms * 1e-3) / 1e9
+                r["hbm_gbs_per_gpu"] = gbs
+                r["frac_of_hbm_peak"] = gbs / peaks["hbm_gbs"]
+            else:
+                tf = nq * npg * FLOPS_PER_PAIR / (ms * 1e-3) / 1e12
+                r["tflops_per_gpu"] = tf
+                r["frac_of_bf16_burst_peak"] = tf / peaks["bf16_tflops"]
+            if n_gpus > 1:
+                r["sharded_check"] = check_sharded_result(torch, dist, one(), s, npg, rank, n_gpus, dev)
+            if mode == xmode:
+                rec.update(r)
+            else:
+                rec[f"exchange_{mode}"] = r
         out[f"q{nq}"] = rec
     return out
 
 
-def exchange_latency(evdr, torch, dev, rank, npg, timed, xmode):
+def exchange_latency(evdr, torch, dev, rank, npg, timed, peer_ok):
     """us per ShardedSearch.topk call on resident (nq, npg) score blocks: ncclAllGather + unpack + merge vs
     the one-kernel peer-memory exchange (only measured when the peer regions were set up)."""
     out = {}
     for nq in (1, 64):
         s = torch.randn((nq, npg), device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
-        for mode in (["nccl", "peer"] if xmode == "peer" else ["nccl"]):
+        for mode in (["nccl", "peer"] if peer_ok else ["nccl"]):
             ss = evdr.ShardedSearch((rank * npg, (rank + 1) * npg), mode=mode)
             out[f"q{nq}_{mode}"] = timed(lambda: ss.topk(s, TOPK), 50, 5) * 1e3
     return out
@@ -492,31 +617,39 @@ def host_corpus_e2e(evdr, torch, corpus, Qh, qmh, host_scores, dev, timed, steps
 
 
 def side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus):
-    """Single-query streaming scan (HBM-bound) and 64-query batches (BASELINE.json configs[3])."""
+    """Single-query streaming scan (HBM-bound), 16 / 32-query batches (the mixed tensor + HBM regime) and
+    64-query batches (BASELINE.json configs[3]); each run long enough (>= ~1.5 s) for its own nvidia-smi
+    clock / power record."""
     out = {}
     npg = pk.n_pages
-    for nq in (1, 64):
+    for nq in (1, 16, 32, 64):
         g = torch.Generator().manual_seed(50 + nq)
         Q = torch.nn.functional.normalize(torch.randn(nq, LQ, D, generator=g), dim=-1).to(dev)
         qm = torch.ones((nq, LQ), dtype=torch.bool, device=dev)
         Qb, qm32 = evdr.pack_queries(Q, qm)
         s = torch.empty((nq, npg), dtype=torch.float32, device=dev)
-        ms_scan = timed(lambda: pk.score_packed(Qb, qm32, out=s), 10, 3)
+        ms0 = timed(lambda: pk.score_packed(Qb, qm32, out=s), 3, 3)
+        reps = int(max(10, min(400, 1500.0 / ms0)))
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
+        ms_scan = timed(lambda: pk.score_packed(Qb, qm32, out=s), reps, 1)
+        clk = sampler.stop()
         ms_search = timed(lambda: search.topk(pk.score_packed(Qb, qm32, out=s), TOPK), 10, 3)
         pages_s = npg / (ms_scan * 1e-3)
-        rec = {"ms_scan": ms_scan, "ms_search_top10": ms_search, "pages_per_s_per_gpu": pages_s,
+        rec = {"ms_scan": ms_scan, "launches_timed": reps, "ms_search_top10": ms_search, "pages_per_s_per_gpu": pages_s,
                "pairs_per_s": nq * npg * n_gpus / (ms_search * 1e-3),
-               "queries_per_s_at_this_corpus": nq / (ms_search * 1e-3), "pages_total": npg * n_gpus}
+               "queries_per_s_at_this_corpus": nq / (ms_search * 1e-3), "pages_total": npg * n_gpus,
+               "clocks": clk}
+        gbs = pages_s * BYTES_PER_PAGE / 1e9
+        tf = nq * npg * FLOPS_PER_PAIR / (ms_scan * 1e-3) / 1e12
         if nq == 1:
-            gbs = pages_s * BYTES_PER_PAGE / 1e9
             rec["roofline"] = {"kernel": "maxsim_tc_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": measured_traffic(nq, npg),
                                "algorithmic_bytes_per_launch": npg * BYTES_PER_PAGE}
         else:
-            tf = nq * npg * FLOPS_PER_PAIR / (ms_scan * 1e-3) / 1e12
             rec["roofline"] = {"kernel": "maxsim_tc_kernel", "bound": "tensor", "achieved": tf,
                                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
-                               "traffic": measured_traffic(nq, npg)}
+                               "hbm_gbs_alongside": gbs, "traffic": measured_traffic(nq, npg)}
         out[f"q{nq}"] = rec
     return out
 

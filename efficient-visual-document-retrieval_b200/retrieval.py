@@ -14,6 +14,7 @@ owns the device memory and the stream.  Inputs on the CPU raise: there is no CPU
 from __future__ import annotations
 
 import os
+import threading
 from abc import ABC, abstractmethod
 from collections import OrderedDict
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
@@ -200,26 +201,49 @@ def maxsim_exact(Q, P, qmask, pmask) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 _PACK_CACHE: "OrderedDict[tuple, PackedPages]" = OrderedDict()
 _PACK_CACHE_SLOTS = int(os.environ.get("EVDR_PACK_CACHE", "2"))
+_PACK_CACHE_LOCK = threading.Lock()
 
 
-def _packed_for(P: torch.Tensor, pmask: torch.Tensor) -> PackedPages:
-    key = (P.data_ptr(), P._version, tuple(P.shape), P.dtype, pmask.data_ptr(), pmask._version,
-           tuple(pmask.shape), pmask.dtype, P.device.index)
-    hit = _PACK_CACHE.get(key) if _PACK_CACHE_SLOTS > 0 else None
-    if hit is not None:
-        _PACK_CACHE.move_to_end(key)
-        return hit
-    if (P.dtype == torch.bfloat16 and P.is_contiguous() and P.shape[1] % _lib.CHUNK == 0
-            and bool(pmask.all().item())):
+def default_precision(P: torch.Tensor) -> str:
+    """Arithmetic of calls that do not name a precision.  The reference up-casts to fp32 and runs an fp32
+    einsum (evaluator/retrieval.py:176-177,195).  A bf16 page tensor is scored as plain bf16 x bf16 -> fp32
+    (its values ARE bf16, only the query is rounded); an fp32 page tensor (the teacher / student tensors of
+    the training scripts) is scored with the bf16x3 split, i.e. the fp32 dot products to ~2^-18 relative, so
+    that teacher and student scores of one step -- and evaluation rankings -- carry the same, near-fp32
+    accuracy.  EVDR_PRECISION=bf16|bf16x3|fp32 overrides."""
+    env = os.environ.get("EVDR_PRECISION")
+    if env:
+        return env
+    return "bf16" if P.dtype == torch.bfloat16 else "bf16x3"
+
+
+def _packed_for(P: torch.Tensor, pmask: torch.Tensor, k_blocks: int = 1) -> PackedPages:
+    """Packed stream of a page tensor, cached for frozen tensors.  The key is storage + in-place version
+    counters, so writes through torch ops invalidate an entry; writes that bypass the counters (``.data``,
+    raw pointers) are not seen -- set EVDR_PACK_CACHE=0 for such callers.  Inference-mode tensors carry no
+    version counter and are never cached."""
+    cacheable = _PACK_CACHE_SLOTS > 0 and not (P.is_inference() or pmask.is_inference())
+    key = None
+    if cacheable:
+        key = (P.data_ptr(), P._version, tuple(P.shape), P.dtype, pmask.data_ptr(), pmask._version,
+               tuple(pmask.shape), pmask.dtype, P.device.index, k_blocks)
+        with _PACK_CACHE_LOCK:
+            hit = _PACK_CACHE.get(key)
+            if hit is not None:
+                _PACK_CACHE.move_to_end(key)
+                return hit
+    if (k_blocks == 1 and P.dtype == torch.bfloat16 and P.is_contiguous() and P.shape[1] % _lib.CHUNK == 0
+            and bool(pmask.all().item())):          # one host sync per cache MISS (frozen corpora: once)
         pk = PackedPages.from_uniform_tokens(P)        # already in stream layout: used in place
     else:
-        pk = PackedPages.from_padded(P, pmask, normalize=False, varlen=False)
-    if _PACK_CACHE_SLOTS > 0:
+        pk = PackedPages.from_padded(P, pmask, normalize=False, varlen=False, k_blocks=k_blocks)
+    if cacheable:
         # hold references so that the key's storage cannot be recycled while cached
         pk._key_refs = (P, pmask)
-        _PACK_CACHE[key] = pk
-        while len(_PACK_CACHE) > _PACK_CACHE_SLOTS:
-            _PACK_CACHE.popitem(last=False)
+        with _PACK_CACHE_LOCK:
+            _PACK_CACHE[key] = pk
+            while len(_PACK_CACHE) > _PACK_CACHE_SLOTS:
+                _PACK_CACHE.popitem(last=False)
     return pk
 
 
@@ -283,12 +307,12 @@ def score_multi_vector_masked(
     (the reference's evaluation loop, mainv2_iter_listwise.py:312-318) come from a host mirror filled by
     ONE device->host copy instead of Q*P synchronisations (EVDR_HOST_MIRROR=0 disables it).
 
-    precision=None | "bf16": tcgen05 path (bf16 operands, fp32 accumulation) whenever D == 128 and
-    Lq <= 32.  Calls that need a gradient use the same tensor-core kernel to FIND the winning page
-    token of every (query token, page) and rescore the winners exactly in fp32 on the original
-    operands, so the student scores of a training step are fp32-exact wherever bf16 and fp32 agree on
-    the winner; the backward is the deterministic closed form of the reference's autograd through
-    those indices.  precision="fp32" (or env EVDR_PRECISION=fp32) and other shapes use the exact fp32
+    precision=None: ``default_precision(P)`` -- plain bf16 operands for a bf16 page tensor, the bf16x3 split
+    (near-fp32 similarities) for an fp32 one; both run on the tcgen05 kernel whenever D == 128 and
+    Lq <= 128.  Calls that need a gradient run ONE bf16x3 pass that yields the scores and the winning page
+    token of every (query token, page); the backward is the deterministic closed form of the reference's
+    autograd through those indices (EVDR_TRAIN_RESCORE=1 additionally rescores the winners in fp32 on the
+    original operands).  precision="fp32" (or env EVDR_PRECISION=fp32) and other shapes use the exact fp32
     kernels throughout.
     """
     if Q.dim() != 3 or P.dim() != 3 or Q.shape[-1] != P.shape[-1]:
@@ -303,7 +327,7 @@ def score_multi_vector_masked(
     npg = P.shape[0]
     if nq == 0 or npg == 0:
         return torch.zeros((nq, npg), dtype=torch.float32, device=Q.device)
-    precision = precision or os.environ.get("EVDR_PRECISION", "bf16")
+    precision = precision or default_precision(P)
     needs_grad = torch.is_grad_enabled() and (Q.requires_grad or P.requires_grad)
     if precision == "fp32" or d != TC_DIM or lq > TC_LQ_MAX:
         out = maxsim_exact(Q, P, qmask, pmask)
@@ -311,7 +335,7 @@ def score_multi_vector_masked(
     if precision == "bf16x3" and not needs_grad:
         # high-fidelity tensor-core mode for operands that are not bf16-representable
         with torch.no_grad():
-            return _ScoreMatrix.wrap(PackedPages.from_padded(P.detach(), pmask, k_blocks=3).score(Q.detach(), qmask))
+            return _ScoreMatrix.wrap(_packed_for(P.detach(), pmask, 3).score(Q.detach(), qmask))
     if needs_grad:
         # training: tensor-core search + fp32 rescoring of the winners, backward through the same indices
         Qf, qm8 = _float_operand(Q), _mask_u8(qmask)
@@ -422,10 +446,13 @@ class BaseVisualRetrieverProcessor(ABC):
             mx = max(blk)
             padded.extend(l < mx for l in blk)
         with torch.no_grad():
-            if d == TC_DIM and lq <= TC_LQ_MAX and os.environ.get("EVDR_PRECISION", "bf16") != "fp32":
+            prec = os.environ.get("EVDR_PRECISION") or (
+                "bf16" if all(p.dtype == torch.bfloat16 for p in ps) else "bf16x3")     # see default_precision
+            if d == TC_DIM and lq <= TC_LQ_MAX and prec != "fp32":
                 # pages: one concatenation, one copy, one ragged pack; a page shorter than its block's longest
                 # gets one extra all-zero token (the reference's padding zeros take part in the max)
-                pk = PackedPages.from_tensor_list(ps, device=device, extra_zero_token=padded)
+                pk = PackedPages.from_tensor_list(ps, device=device, extra_zero_token=padded,
+                                                  k_blocks=3 if prec == "bf16x3" else 1)
                 scores = pk.score(Q, qm)
             else:
                 lp = max(l + (1 if pad else 0) for l, pad in zip(lens, padded))
@@ -462,8 +489,11 @@ class CustomRetrievalEvaluator:
 
     # fast path: scores already on the device -------------------------------------------------
     def evaluate_scores(self, scores: torch.Tensor, qrel_off, qrel_ids, qrel_rels,
-                        tie_rank: Optional[torch.Tensor] = None) -> Dict[str, Dict[str, float]]:
-        """scores (nq, np) fp32 on device; qrels as CSR over column indices."""
+                        tie_rank: Optional[torch.Tensor] = None,
+                        n_judged: Optional[int] = None) -> Dict[str, Dict[str, float]]:
+        """scores (nq, np) fp32 on device; qrels as CSR over column indices.  ``n_judged`` is the MRR
+        denominator -- ``len(relevant_docs)`` of the dict signature (mteb's mrr divides by the number of
+        JUDGED queries, scored or not); it defaults to the number of scored rows."""
         kmax = min(max(self.k_values), _lib.TOPK_MAX)
         if max(self.k_values) > _lib.TOPK_MAX:
             raise NotImplementedError(f"k_values above {_lib.TOPK_MAX} are not supported")
@@ -471,7 +501,7 @@ class CustomRetrievalEvaluator:
         if tie_rank is not None:  # mteb's MRR sorts stably: ties in column order
             _, ids2 = topk(scores, kmax, tie_rank=None)
             m[4] = retrieval_metrics(ids2, qrel_off, qrel_ids, qrel_rels, self.k_values)[4]
-        return self._format(m.cpu())
+        return self._format(m.cpu(), mrr_den=n_judged)
 
     def _format(self, m: torch.Tensor, mrr_den: Optional[int] = None) -> Dict[str, Dict[str, float]]:
         def mean(row, den=None):  # Python float sum like mteb (sum(list)/len)

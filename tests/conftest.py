@@ -24,3 +24,10 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+@pytest.fixture
+def plain_bf16(monkeypatch):
+    """Pin calls that do not name a precision to the plain bf16 tcgen05 flavours (the default for fp32 page
+    tensors is the bf16x3 split, retrieval.default_precision); explicit precision= arguments still win."""
+    monkeypatch.setenv("EVDR_PRECISION", "bf16")

@@ -338,9 +338,14 @@ def test_evaluate_scores_fast_path(evdr, cuda):
             rels.append(r)
         off.append(len(ids))
     ev = evdr.CustomRetrievalEvaluator()
-    got = ev.evaluate_scores(dense.to(cuda), torch.tensor(off), torch.tensor(ids), torch.tensor(rels), tie_rank=tie.to(cuda))
+    got = ev.evaluate_scores(dense.to(cuda), torch.tensor(off), torch.tensor(ids), torch.tensor(rels), tie_rank=tie.to(cuda),
+                             n_judged=len(qrels))
     want = ev.compute_mteb_metrics(qrels, results)
     assert got == want
+    # without n_judged the MRR denominator is the number of scored rows; everything else is unchanged
+    got_scored = ev.evaluate_scores(dense.to(cuda), torch.tensor(off), torch.tensor(ids), torch.tensor(rels),
+                                    tie_rank=tie.to(cuda))
+    assert {k: v for k, v in got_scored.items() if k != "mRR"} == {k: v for k, v in want.items() if k != "mRR"}
 
 
 def test_from_object_arrays_matches_padded_pipeline(evdr, cuda):

@@ -13,7 +13,7 @@ from oracle import maxsim_oracle as mo
 from oracle import trec_oracle as to
 from tests import _util as U
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("plain_bf16")]
 
 
 @pytest.mark.parametrize("name", ["full1030", "comp64", "varlen", "student_mf5", "lq1"])

@@ -1,6 +1,8 @@
-"""GPU parity at the shapes of BASELINE.json's configs, against a plain PyTorch fp32 restatement of
-the op run on the same device (the reference's own eager path is the bar on a B200), and
-a training step through the exact kernels' backward (config 5)."""
+"""GPU parity at the shapes of BASELINE.json's configs against the reference's OWN
+``score_multi_vector_masked`` (unmodified evaluator/retrieval.py:166-213 staged under baseline/_ref by
+tools/stage_reference.py) run torch-eager on the same device -- the reference's eager path is the bar on a
+B200, SURVEY 2.1 -- and a training step through the backward (config 5).  Only if the staged reference is
+absent does the test-local restatement below stand in (a warning says so)."""
 import numpy as np
 import pytest
 import torch
@@ -8,10 +10,30 @@ import torch.nn.functional as F
 
 from tests import _util as U
 
+from baseline import ref as reference
+
 pytestmark = pytest.mark.gpu
 
 
 def torch_maxsim(Q, P, qmask, pmask, chunk=32):
+    """The comparator: the reference's own function when staged, else the restatement."""
+    if reference.available():
+        return reference.scorer_module().score_multi_vector_masked(Q, P, qmask, pmask, chunk)
+    import warnings
+    warnings.warn("baseline/_ref is not staged: comparing with the test-local restatement of the reference")
+    return _torch_maxsim_restated(Q, P, qmask, pmask, chunk)
+
+
+def test_comparator_is_the_unmodified_reference():
+    """The staged files are byte-identical to the manifest written when they were copied from the reference."""
+    if not reference.available():
+        pytest.skip(reference.why_unavailable())
+    reference.verify()
+    fn = reference.scorer_module().score_multi_vector_masked
+    assert "baseline/_ref/evaluator/retrieval.py" in fn.__code__.co_filename.replace("\\", "/")
+
+
+def _torch_maxsim_restated(Q, P, qmask, pmask, chunk=32):
     """Plain torch fp32 MaxSim with the reference's semantics (evaluator/retrieval.py:166-213),
     written for the tests: one matmul per page chunk, -1e4 fill, max, has-token and query masks, sum."""
     Q, P = Q.float(), P.float()
@@ -57,7 +79,9 @@ def test_config2_vidore_shapes(evdr, cuda, name, npg, nq, lp):
 
 
 def listwise_distillation_loss(score_s, score_t, k=10, temperature=1.0):
-    """criterion.py:114-142 restated for the test (the loss itself stays in torch)."""
+    """The reference's own criterion.py:114-142 when staged, else restated for the test."""
+    if reference.available():
+        return reference.criterion_module().listwise_distillation_loss(score_s, score_t, k=k, temperature=temperature)
     score_t = score_t.detach()
     log_ps = F.log_softmax(score_s / temperature, dim=1)
     pt = F.softmax(score_t / temperature, dim=1)
@@ -219,11 +243,15 @@ def test_bf16x3_high_fidelity_mode(evdr, cuda, nq, npg, lp):
     qm = torch.rand(nq, 32, generator=g, device=cuda) > 0.1
     exact = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
     x3 = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="bf16x3")
-    bf = evdr.score_multi_vector_masked(Q, P, qm, pm)
+    bf = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="bf16")
     e3 = ((x3 - exact).abs() / exact.abs().clamp_min(1)).max().item()
     e1 = ((bf - exact).abs() / exact.abs().clamp_min(1)).max().item()
     assert e3 < 5e-6, e3
     assert e1 < 1e-3 and e3 < e1
+    # fp32 page tensors take the split by default (retrieval.default_precision); a bf16 page tensor plain bf16
+    assert torch.equal(evdr.score_multi_vector_masked(Q, P, qm, pm), x3)
+    assert torch.equal(evdr.score_multi_vector_masked(Q, P.bfloat16(), qm, pm),
+                       evdr.score_multi_vector_masked(Q, P.bfloat16(), qm, pm, precision="bf16"))
 
 
 def test_hard_token_mining_matches_reference_loop(evdr, cuda):

@@ -9,7 +9,7 @@ import torch
 from oracle import maxsim_oracle as mo
 from tests import _util as U
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("plain_bf16")]
 
 
 def _need(cuda, gib):

@@ -8,7 +8,7 @@ import torch
 from oracle import maxsim_oracle as mo
 from tests import _util as U
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("plain_bf16")]
 
 _rng = np.random.default_rng(20261018)
 _NQ = [1, 2, 4, 5, 7, 8, 9, 12, 15, 16, 17, 31, 32, 33, 47, 60, 61, 64, 65, 99, 128, 140]

@@ -7,7 +7,7 @@ import ctypes as C
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("plain_bf16")]
 
 SENT_F = -12345.678
 SENT_I = -987654321
