@@ -539,19 +539,40 @@ def corpus_1m(evdr, torch, dist, dev, rank, n_gpus, peaks, timed, xmode="nccl", 
 
             def one():
                 Qb, qm32 = evdr.pack_queries(Q, qm)
-                return search.topk(pk.score_packed(Qb, qm32, out=s), TOPK)
+                return search.search_packed(pk, Qb, qm32, TOPK)     # scan (+ fused top-k) + exchange + merge
 
             # end to end: the query batch starts in pinned host memory, the top-10 (scores, ids) end there
             def one_e2e():
                 Qb, qm32 = evdr.pack_queries(Qh.to(dev, non_blocking=True), qmh.to(dev, non_blocking=True))
-                ts, ti = search.topk(pk.score_packed(Qb, qm32, out=s), TOPK)
+                ts, ti = search.search_packed(pk, Qb, qm32, TOPK)
                 hs.copy_(ts, non_blocking=True)
                 hi_.copy_(ti, non_blocking=True)
 
             ms = timed(one, 10, 3)
             ms_e2e = timed(one_e2e, 10, 3)
             r = {"ms_per_batch": ms, "top10_qps": nq / (ms * 1e-3), "pairs_per_s": nq * total / (ms * 1e-3),
-                 "ms_per_batch_e2e": ms_e2e, "top10_qps_e2e": nq / (ms_e2e * 1e-3)}
+                 "ms_per_batch_e2e": ms_e2e, "top10_qps_e2e": nq / (ms_e2e * 1e-3),
+                 "call": "pack_queries + evdr_sharded_search (scan" + (" with the top-10 fused into its epilogue"
+                         if nq <= 8 else "") + f", {mode} exchange, merge)"}
+            if nq == 1:
+                # the same sequence captured once as a CUDA graph and replayed (host copies in the timed region)
+                try:
+                    gs = evdr.GraphedSearch(search, pk, nq, TOPK)
+
+                    def one_graph():
+                        ts, ti = gs(Qh, qmh)
+                        hs.copy_(ts, non_blocking=True)
+                        hi_.copy_(ti, non_blocking=True)
+
+                    ms_g = timed(one_graph, 10, 3)
+                    r["ms_per_batch_graph_e2e"] = ms_g
+                    r["top10_qps_graph_e2e"] = nq / (ms_g * 1e-3)
+                    del gs
+                except Exception as e:
+                    r["graph_error"] = repr(e)
+                # unfused reference point: scores row + two-stage top-k + exchange
+                ms_u = timed(lambda: search.topk(pk.score_packed(*evdr.pack_queries(Q, qm), out=s), TOPK), 10, 3)
+                r["ms_per_batch_unfused"] = ms_u
             if nq == 1:
                 gbs = npg * BYTES_PER_PAGE / (ms * 1e-3) / 1e9
                 r["hbm_gbs_per_gpu"] = gbs
@@ -561,6 +582,7 @@ def corpus_1m(evdr, torch, dist, dev, rank, n_gpus, peaks, timed, xmode="nccl", 
                 r["tflops_per_gpu"] = tf
                 r["frac_of_bf16_burst_peak"] = tf / peaks["bf16_tflops"]
             if n_gpus > 1:
+                pk.score_packed(*evdr.pack_queries(Q, qm), out=s)            # score rows for the check
                 r["sharded_check"] = check_sharded_result(torch, dist, one(), s, npg, rank, n_gpus, dev)
             if mode == xmode:
                 rec.update(r)
@@ -634,7 +656,7 @@ def side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus
         sampler.start()
         ms_scan = timed(lambda: pk.score_packed(Qb, qm32, out=s), reps, 1)
         clk = sampler.stop()
-        ms_search = timed(lambda: search.topk(pk.score_packed(Qb, qm32, out=s), TOPK), 10, 3)
+        ms_search = timed(lambda: search.search_packed(pk, Qb, qm32, TOPK), 10, 3)
         pages_s = npg / (ms_scan * 1e-3)
         rec = {"ms_scan": ms_scan, "launches_timed": reps, "ms_search_top10": ms_search, "pages_per_s_per_gpu": pages_s,
                "pairs_per_s": nq * npg * n_gpus / (ms_search * 1e-3),

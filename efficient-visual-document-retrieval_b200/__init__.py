@@ -20,7 +20,7 @@ from .mining import hard_token_argmax, hard_tokens
 from .normalize import l2_normalize, l2_normalize_masked
 from .retrieval import (BaseVisualRetrieverProcessor, CustomRetrievalEvaluator, TeacherScoreTable, maxsim_exact,
                         score_multi_vector_masked)
-from .sharded import ShardedSearch, gather_score_rows, init_nccl_comm, init_peer_exchange, partition_pages
+from .sharded import GraphedSearch, ShardedSearch, gather_score_rows, init_nccl_comm, init_peer_exchange, partition_pages
 from .topk import retrieval_metrics, topk as top_k, topk_merge, topk_metrics
 
 __version__ = "0.1.0"

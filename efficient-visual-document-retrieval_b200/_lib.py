@@ -21,7 +21,7 @@ TC_LQ_MAX = 128      # longer queries are scored as up to 4 groups of 32 tokens
 TOPK_MAX = 128
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 _handles: dict[int, C.c_void_p] = {}
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
@@ -60,6 +60,7 @@ _SIGNATURES = {
     "evdr_peer_connect": ([_vp, _vp], _i),
     "evdr_peer_world": ([_vp], _i),
     "evdr_peer_sharded_topk": ([_vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp], _i),
+    "evdr_sharded_search": ([_vp, _vp, _vp, _i, _vp, _i64, _vp, _i, _i64, _i, _i64, _i, _vp, _vp, _vp], _i),
     "evdr_l2norm_fwd": ([_vp, _vp, _vp, _i64, _i, _vp, _vp], _i),
     "evdr_l2norm_bwd": ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp], _i),
     "evdr_rank_gap": ([_vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
@@ -123,10 +124,13 @@ def handle(device: torch.device | int) -> C.c_void_p:
     idx = device if isinstance(device, int) else (device.index if device.index is not None else torch.cuda.current_device())
     h = _handles.get(idx)
     if h is None:
-        lib = load()
-        out = _vp()
-        check(lib.evdr_create(idx, C.byref(out)), "evdr_create")
-        _handles[idx] = h = out
+        with _lock:                      # two threads must not create two handles for one device
+            h = _handles.get(idx)
+            if h is None:
+                lib = load()
+                out = _vp()
+                check(lib.evdr_create(idx, C.byref(out)), "evdr_create")
+                _handles[idx] = h = out
     return h
 
 

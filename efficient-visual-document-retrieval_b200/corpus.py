@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import CHUNK, TC_DIM, TC_LQ, TC_LQ_MAX
+from ._lib import CHUNK, TC_DIM, TC_LQ, TC_LQ_MAX, TOPK_MAX
 
 
 def _mask_u8(mask: torch.Tensor) -> torch.Tensor:
@@ -259,6 +259,19 @@ class PackedPages:
     def search(self, Q: torch.Tensor, qmask: torch.Tensor, k: int = 10):
         """Top-k pages per query: (scores (nq,k) fp32, ids (nq,k) int64 global page ids)."""
         from .topk import topk
+        if self.k_blocks == 1 and Q.shape[1] <= TC_LQ and k <= TOPK_MAX:
+            # one library call; for <= 8 queries on long pages the top-k is folded into the scan's epilogue
+            Qb, qm32 = pack_queries(Q, qmask)
+            nq = Qb.shape[0]
+            top_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            top_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            lib = _lib.load()
+            _lib.check(lib.evdr_sharded_search(_lib.handle(self.device), Qb.data_ptr(), qm32.data_ptr(), nq,
+                                               self.tokens.data_ptr(), self.tokens.shape[0], self.chunk_off.data_ptr(),
+                                               self.n_pages, self.total_chunks, k, self.page_offset, 0,
+                                               top_s.data_ptr(), top_i.data_ptr(), _lib.stream_ptr(self.device)),
+                       "evdr_sharded_search")
+            return top_s, top_i
         scores = self.score(Q, qmask)
         return topk(scores, k, id_offset=self.page_offset)
 

@@ -23,7 +23,7 @@ PKG = CSRC.parent
 OUT = PKG / "libevdr.so"
 BUILD = CSRC / "build"
 SOURCES = ["evdr_core.cu", "maxsim_simt.cu", "pack.cu", "topk.cu", "sharded.cu", "losses.cu", "train.cu", "maxsim_tc.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", "../../include/evdr.h"]
+HEADERS = ["common.cuh", "ptx.cuh", "topk_dev.cuh", "../../include/evdr.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

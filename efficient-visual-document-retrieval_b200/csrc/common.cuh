@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -64,7 +65,10 @@ struct evdr_handle {
   // scheduler counters of the tensor-core kernel: a ring of device ints owned by the handle (one per
   // launch, zeroed on the launch stream), so the hot path never allocates
   int* sched_ring;
-  unsigned sched_next;
+  std::atomic<unsigned> sched_next;
+  // stream-ordered scratch comes from a pool OWNED by the handle (the device's default pool and its
+  // release threshold, which other libraries in the process may rely on, are left alone)
+  cudaMemPool_t pool;
   // multi-GPU
   void* nccl_comm;  // ncclComm_t
   int rank, world;
@@ -75,8 +79,34 @@ struct evdr_handle {
   unsigned char** peer_ptrs_dev;
   void* peer_opened[16];
   int peer_world, peer_rank, peer_cap;
-  unsigned peer_seq;
+  unsigned* peer_err_host;              // pinned + mapped: non-zero after a failed wait (sticky)
+  unsigned* peer_err_dev;               // the same word as seen from the device
+  unsigned long long peer_timeout_ns;   // bound of one wait in the exchange kernel (0 = unbounded)
 };
+
+namespace evdr {
+// internal cross-file entry points (not part of the C ABI)
+// maxsim_tc.cu: scan with the top-k fused into the epilogue; EVDR_ERR_UNSUPPORTED (no message) when the
+// launch would have more than one query group or needs the short-page epilogue.  cand_* hold
+// nq * n_cta * k entries on return (n_cta <= sm_count).
+int scan_topk(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq, const void* tokens, int64_t n_tokens,
+              const int32_t* chunk_off, int np, int64_t total_chunks, int k, int64_t id_offset, float* cand_s,
+              long long* cand_i, int* n_cta, cudaStream_t st);
+// topk.cu: k <= 32 best of (nq, ncand) candidate rows, one CTA per query, one launch
+int select_candidates(evdr_handle* h, const float* cand_s, const long long* cand_i, int nq, int ncand, int k,
+                      float* top_s, long long* top_i, cudaStream_t st);
+// sharded.cu
+int peer_exchange(evdr_handle* h, const float* cand_s, const long long* cand_i, int nq, int ncand, int k,
+                  float* top_scores, long long* top_ids, cudaStream_t st);
+}  // namespace evdr
+
+namespace evdr {
+// stream-ordered workspace from the handle's private pool (freed with cudaFreeAsync)
+template <typename T>
+inline cudaError_t ws_alloc(evdr_handle* h, T** p, size_t bytes, cudaStream_t st) {
+  return cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), bytes, h->pool, st);
+}
+}  // namespace evdr
 
 #define EVDR_REQUIRE_HANDLE(h)                                                        \
   do {                                                                                \

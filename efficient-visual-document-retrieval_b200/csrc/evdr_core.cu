@@ -41,8 +41,7 @@ int evdr_create(int device, evdr_handle** out) {
     return evdr::set_error(EVDR_ERR_CUDA,
                            "device %d is sm_%d%d; libevdr is built for sm_100a (B200) only",
                            device, prop.major, prop.minor);
-  evdr_handle* h = new evdr_handle();
-  memset(h, 0, sizeof(*h));
+  evdr_handle* h = new evdr_handle();   // value-initialised: all members zero
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->cc_major = prop.major;
@@ -63,14 +62,25 @@ int evdr_create(int device, evdr_handle** out) {
     delete h;
     return evdr::set_error(EVDR_ERR_CUDA, "cudaMalloc of the scheduler ring failed");
   }
-  h->sched_next = 0;
-  // Stream-ordered scratch (cudaMallocAsync) is used for small temporaries.  By default the pool
-  // gives its memory back to the driver at every synchronisation, which turns each later
-  // allocation into a millisecond-scale driver call: keep the pool's memory cached instead.
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t keep = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  cudaMemset(h->sched_ring, 0, sizeof(int) * EVDR_SCHED_RING);   // every user hands its slot back zeroed
+  // Stream-ordered scratch for small temporaries: a PRIVATE pool whose memory stays cached up to a bounded
+  // threshold (a pool at the default threshold 0 gives everything back to the driver at every
+  // synchronisation, which turns each later allocation into a millisecond-scale driver call -- a per-step
+  // loss.item() made every scorer call 20+ ms).  EVDR_POOL_KEEP_MB overrides the 2 GiB default.
+  {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&h->pool, &props) != cudaSuccess) {
+      cudaFree(h->sched_ring);
+      delete h;
+      return evdr::set_error(EVDR_ERR_CUDA, "cudaMemPoolCreate failed");
+    }
+    uint64_t keep = 2048ull << 20;
+    if (const char* e = getenv("EVDR_POOL_KEEP_MB")) keep = strtoull(e, nullptr, 10) << 20;
+    cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   *out = h;
   return EVDR_OK;

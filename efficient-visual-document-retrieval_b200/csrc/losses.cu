@@ -142,6 +142,7 @@ liscore_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __re
     row_loss[2 * b + 1] = se;
     __threadfence();
     last = (atomicAdd(done, 1) == B - 1);
+    if (last) *done = 0;                    // hand the counter slot back zeroed (ring slots are shared)
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
@@ -192,6 +193,7 @@ pairwise_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __r
     part[blockIdx.y * gridDim.x + blockIdx.x] = acc;
     __threadfence();
     last = (atomicAdd(done, 1) == nblk - 1);
+    if (last) *done = 0;                    // hand the counter slot back zeroed (ring slots are shared)
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
@@ -259,6 +261,7 @@ lambda_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __res
     part[blockIdx.y * gridDim.x + blockIdx.x] = acc;
     __threadfence();
     last = (atomicAdd(done, 1) == nblk - 1);
+    if (last) *done = 0;                    // hand the counter slot back zeroed (ring slots are shared)
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
@@ -329,6 +332,7 @@ ranknce_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __re
     row_loss[2 * b + 1] = rk;
     __threadfence();
     last = (atomicAdd(done, 1) == B - 1);
+    if (last) *done = 0;                    // hand the counter slot back zeroed (ring slots are shared)
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
@@ -345,9 +349,10 @@ ranknce_kernel(const float* __restrict__ sc_s, long long ld_s, const float* __re
 }
 
 static int next_counter(evdr_handle* h, cudaStream_t st, int** out) {
-  int* c = h->sched_ring + (h->sched_next++ % EVDR_SCHED_RING);
-  EVDR_CUDA(cudaMemsetAsync(c, 0, sizeof(int), st));
-  *out = c;
+  // slots start zeroed (evdr_create) and every user hands its slot back zeroed, so no memset is needed;
+  // the atomic index keeps two host threads that (against the contract) share a handle on distinct slots
+  (void)st;
+  *out = h->sched_ring + (h->sched_next.fetch_add(1, std::memory_order_relaxed) % EVDR_SCHED_RING);
   return EVDR_OK;
 }
 

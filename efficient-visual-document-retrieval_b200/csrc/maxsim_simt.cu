@@ -603,7 +603,7 @@ int evdr_maxsim_bwd(evdr_handle* h, const float* gout, const void* Q, int q_dtyp
   }
   if (dQ) {
     uint8_t* has = nullptr;
-    EVDR_CUDA(cudaMallocAsync(&has, np, st));
+    EVDR_CUDA(evdr::ws_alloc(h, &has, np, st));
     has_page_kernel<<<(np + 7) / 8, 256, 0, st>>>(pmask, np, lp, has);
     EVDR_LAUNCH_CHECK("has_page_kernel");
     if (p_dtype == EVDR_F32)

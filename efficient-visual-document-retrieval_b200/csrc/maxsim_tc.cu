@@ -51,6 +51,12 @@ struct TcParams {
   int lq;                     // AM variant: real query length (rows >= lq are padding)
   int* sched;                 // dynamic scheduler: global item counter (zeroed per launch); CG2: unused
   const __nv_bfloat16* qb;    // TA variant: packed queries [nq, 32, 128] in global memory (staged to TMEM)
+  // TK variant (fused local top-k, one query group): per (query, CTA) the k best pages this CTA scored,
+  // best first, padded with (-inf, -1): cand_s / cand_i [nq][gridDim.x][tk_k]; ids are page + id_offset
+  float* cand_s;
+  long long* cand_i;
+  int tk_k;
+  long long id_offset;
 };
 
 // KB = number of 128-wide K blocks of the operands: 1 = plain bf16; 3 = the bf16x3 split
@@ -91,8 +97,12 @@ struct TcCfg {
 // EW = number of epilogue warps: 4 (one group, TMEM buffers alternate per pass) or 8 (two groups of 4;
 // requires R == 2: pass (tile t, query tile r) always uses TMEM buffer r and is drained by group r, so
 // each group owns one query tile's running state and has two MMA periods per pass).
+// TK ("top-k"): launches with ONE query group (<= 4 * R queries: the latency path) keep, per epilogue warp,
+// the k <= 32 best (score, page) of its query in REGISTERS (lane j = j-th best; an insertion is one ballot
+// and two shuffle-ups, and only happens when a page beats the current k-th) and write them once at the
+// end, so that only k candidates per (query, CTA) leave the SM -- the (nq, np) score row is optional.
 template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4,
-          bool TA = false>
+          bool TA = false, bool TK = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                  const TcParams prm) {
@@ -108,6 +118,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert((BN / 32) % 2 == 0, "the drain loop handles 32-column groups in pairs");
   static_assert(EW == 4 || (EW == 8 && R == 2 && !CG2), "8 epilogue warps need R == 2, single-CTA");
+  static_assert(!TK || (!CG2 && !AM && !SP && KB == 1), "fused top-k: single-CTA bf16 scoring flavours, long-page epilogue");
   constexpr uint32_t IDESC = make_idesc_bf16(CG2 ? 256 : 128, BN);
   constexpr int CH_PER_TILE = BN / EVDR_CHUNK;
 
@@ -185,6 +196,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         } else {
           mbar_wait(bar_s_empty(sslot), sphase ^ 1);
           const int v = atomicAdd(prm.sched, 1);
+          // every CTA draws exactly one terminal value (>= n_items); the CTA drawing the last of them
+          // hands the counter back zeroed, so the next launch on this slot needs no memset
+          if (v == n_items + n_units - 1) atomicExch(prm.sched, 0);
           item_ring[sslot] = v;
           mbar_arrive(bar_s_full(sslot));
           if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
@@ -306,6 +320,11 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     int qidx[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { qm[r] = 0.f; qidx[r] = -1; }
+    // TK: this warp's register list per resident query tile (entry `lane`) and the score to beat
+    float tk_s[TK ? R : 1], tk_thr[TK ? R : 1];
+    int tk_p[TK ? R : 1];
+#pragma unroll
+    for (int r = 0; r < (TK ? R : 1); ++r) { tk_s[r] = -INFINITY; tk_thr[r] = -INFINITY; tk_p[r] = -1; }
     const uint32_t t_empty0 = CG2 ? mapa_u32(bar_t_empty(0), 0) : bar_t_empty(0);
     const uint32_t t_empty1 = CG2 ? mapa_u32(bar_t_empty(1), 0) : bar_t_empty(1);
     auto release_tmem = [&](int buf) {
@@ -458,8 +477,22 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                 pstart = pe;
                 bc = pe;
               } else {
-                const float s = warp_sum(rm * qm[r]);
-                if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
+                const float s = warp_sum(rm * qm[r]);        // every lane holds the sum
+                if constexpr (TK) {
+                  if (prm.out != nullptr && lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
+                  // pages arrive in ascending order within a CTA (items are drawn from an increasing counter),
+                  // so an equal score never displaces an entry: strict '>' keeps (score desc, page asc)
+                  if (s > tk_thr[r]) {
+                    const int pos = __popc(__ballot_sync(0xffffffffu, tk_s[r] >= s));
+                    const float us = __shfl_up_sync(0xffffffffu, tk_s[r], 1);
+                    const int up = __shfl_up_sync(0xffffffffu, tk_p[r], 1);
+                    if (lane == pos) { tk_s[r] = s; tk_p[r] = p; }
+                    else if (lane > pos) { tk_s[r] = us; tk_p[r] = up; }
+                    tk_thr[r] = __shfl_sync(0xffffffffu, tk_s[r], prm.tk_k - 1);
+                  }
+                } else {
+                  if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
+                }
               }
               rm = -INFINITY;
               ++p;
@@ -579,6 +612,19 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         }
       }
     }
+    if constexpr (TK) {
+      // one query group: query tile r of this CTA is tile r of the launch whatever items it drew (a CTA
+      // that drew none writes pure padding, so every (query, CTA) slot of the candidate buffer is defined)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int q = r * 4 + quad;
+        if ((EW == 4 || r == egrp) && q < prm.nq && lane < prm.tk_k) {
+          const size_t o = ((size_t)q * gridDim.x + blockIdx.x) * prm.tk_k + lane;
+          prm.cand_s[o] = tk_s[r];
+          prm.cand_i[o] = tk_p[r] >= 0 ? (long long)tk_p[r] + prm.id_offset : -1LL;
+        }
+      }
+    }
   }
 
   // teardown: in pair mode the peer's shared memory / TMEM must stay alive until both CTAs are done
@@ -608,7 +654,7 @@ static int encode_2d_bf16(evdr_handle* h, CUtensorMap* tm, const void* base, uin
 }
 
 template <int R, int BN, int STAGES, bool CG2, bool AM = false, int KB = 1, bool SP = false, int EW = 4,
-          bool TA = false>
+          bool TA = false, bool TK = false>
 static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens,
                      TcParams prm, cudaStream_t st) {
   using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW, TA>;
@@ -618,7 +664,7 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   if (rc != EVDR_OK) return rc;
   rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, KB, "page tokens");
   if (rc != EVDR_OK) return rc;
-  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP, EW, TA>;
+  auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP, EW, TA, TK>;
   if ((size_t)S::TOTAL > h->smem_optin)
     return set_error(EVDR_ERR_UNSUPPORTED, "tensor-core kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -642,9 +688,10 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
   prm.sched = nullptr;
-  if (!CG2) {  // this launch's item counter: next slot of the handle's ring, zeroed on the stream
-    prm.sched = h->sched_ring + (h->sched_next++ % EVDR_SCHED_RING);
-    EVDR_CUDA(cudaMemsetAsync(prm.sched, 0, sizeof(int), st));
+  if (!CG2) {
+    // this launch's item counter: next slot of the handle's ring.  Slots start zeroed (evdr_create) and the
+    // kernel hands its slot back zeroed (the CTA that draws the last terminal value resets it)
+    prm.sched = h->sched_ring + (h->sched_next.fetch_add(1, std::memory_order_relaxed) % EVDR_SCHED_RING);
   }
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmQ, tmP, prm);
   if (le != cudaSuccess)
@@ -656,15 +703,24 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
 
 using namespace evdr;
 
+// fused top-k request of a dispatch (evdr::scan_topk): candidate buffers in, CTA count out
+struct TkRequest {
+  float* cand_s;
+  long long* cand_i;
+  int k;
+  long long id_offset;
+  int n_cta;
+};
+
 static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,
                            const void* tokens, int64_t n_tokens, const int32_t* chunk_off, int np,
                            int64_t total_chunks, int pages_per_item, float* out, int64_t out_ld,
-                           int32_t* argmax, int lq, int k_blocks, void* stream) {
+                           int32_t* argmax, int lq, int k_blocks, void* stream, TkRequest* tk = nullptr) {
   if (k_blocks != 1 && k_blocks != 3)
     return set_error(EVDR_ERR_INVALID, "evdr_maxsim_packed: k_blocks=%d (1 = bf16, 3 = bf16x3 split)", k_blocks);
   EVDR_REQUIRE_HANDLE(h);
-  EVDR_CHECK_ARG(Qb && qmask32 && tokens && chunk_off && (out || argmax), "evdr_maxsim_packed: null pointer");
-  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && (argmax || out_ld >= np), "evdr_maxsim_packed: bad shape nq=%d np=%d ld=%lld",
+  EVDR_CHECK_ARG(Qb && qmask32 && tokens && chunk_off && (out || argmax || tk), "evdr_maxsim_packed: null pointer");
+  EVDR_CHECK_ARG(nq >= 1 && np >= 1 && (argmax || tk || out_ld >= np), "evdr_maxsim_packed: bad shape nq=%d np=%d ld=%lld",
                  nq, np, (long long)out_ld);
   EVDR_CHECK_ARG(total_chunks >= np && n_tokens >= total_chunks * EVDR_CHUNK,
                  "evdr_maxsim_packed_fwd: token stream (%lld) shorter than %lld chunks",
@@ -672,7 +728,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   EVDR_CHECK_ARG(n_tokens < (1LL << 31), "evdr_maxsim_packed_fwd: more than 2^31 tokens per shard");
   EVDR_CHECK_ARG(((uintptr_t)Qb & 15) == 0 && ((uintptr_t)tokens & 15) == 0,
                  "evdr_maxsim_packed_fwd: operands must be 16-byte aligned for TMA");
-  TcParams prm;
+  TcParams prm = {};
   prm.qmask32 = qmask32;
   prm.chunk_off = chunk_off;
   prm.out = out;
@@ -761,6 +817,21 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   prm.g_rem = prm.nqt % n_qgroups;
   prm.stream_hint = (n_qgroups == 1) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tk) {
+    // the top-k is folded into the scan when every CTA keeps the same queries for the whole launch (one query
+    // group: <= 4 queries, or 5-8 with the query tiles in TMEM) and the long-page epilogue is used
+    const bool r1 = !pair && !argmax && k_blocks == 1 && prm.nqt == 1;
+    const bool ta2 = want_ta && !short_pages && n_qgroups == 1;
+    if (!(r1 || ta2) || tk->k > 32) return EVDR_ERR_UNSUPPORTED;
+    const long long n_items = (long long)prm.n_pblocks * prm.n_qgroups;
+    tk->n_cta = (int)(n_items < h->sm_count ? n_items : h->sm_count);
+    prm.cand_s = tk->cand_s;
+    prm.cand_i = tk->cand_i;
+    prm.tk_k = tk->k;
+    prm.id_offset = tk->id_offset;
+    if (ta2) return launch_tc<2, 192, 4, false, false, 1, false, 8, true, true>(h, Qb, tokens, n_tokens, prm, st);
+    return launch_tc<1, 256, 3, false, false, 1, false, 4, false, true>(h, Qb, tokens, n_tokens, prm, st);
+  }
   if (k_blocks == 3) {
     if (argmax) return launch_tc<1, 64, 2, false, true, 3>(h, Qb, tokens, n_tokens, prm, st);
     return launch_tc<1, 64, 2, false, false, 3>(h, Qb, tokens, n_tokens, prm, st);
@@ -782,6 +853,16 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   if (R == 1) return launch_tc<1, 256, 3, false>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 2) return launch_tc<2, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
   return launch_tc<3, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
+}
+
+int evdr::scan_topk(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq, const void* tokens,
+                    int64_t n_tokens, const int32_t* chunk_off, int np, int64_t total_chunks, int k,
+                    int64_t id_offset, float* cand_s, long long* cand_i, int* n_cta, cudaStream_t st) {
+  TkRequest tk = {cand_s, cand_i, k, id_offset, 0};
+  const int rc = packed_dispatch(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, 0, nullptr, 0,
+                                 nullptr, EVDR_TC_LQ, 1, st, &tk);
+  *n_cta = tk.n_cta;
+  return rc;
 }
 
 extern "C" int evdr_maxsim_packed_fwd(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,

@@ -359,7 +359,7 @@ static int pack_plan_impl(evdr_handle* h, const uint8_t* pmask, const long long*
   EVDR_CHECK_ARG(!varlen || pmask, "evdr_pack_plan: varlen needs pmask");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* nch = nullptr;
-  EVDR_CUDA(cudaMallocAsync(&nch, sizeof(int32_t) * (size_t)np, st));
+  EVDR_CUDA(evdr::ws_alloc(h, &nch, sizeof(int32_t) * (size_t)np, st));
   plan_len_kernel<<<(np + 7) / 8, 256, 0, st>>>(pmask, in_off, np, lp, varlen, nch);
   EVDR_LAUNCH_CHECK("plan_len_kernel");
   plan_scan_kernel<<<1, 1024, 0, st>>>(nch, np, chunk_off);

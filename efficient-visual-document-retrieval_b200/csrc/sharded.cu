@@ -4,7 +4,10 @@
 // library carries no link-time NCCL dependency and shares torch's libnccl.so.2.
 #include <dlfcn.h>
 
+#include <mutex>
+
 #include "common.cuh"
+#include "topk_dev.cuh"
 
 namespace evdr {
 
@@ -24,18 +27,18 @@ struct NcclApi {
 
 static NcclApi* nccl_api() {
   static NcclApi api = {};
-  static bool tried = false;
-  if (tried) return api.ok ? &api : nullptr;
-  tried = true;
-  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!lib) return nullptr;
-  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
-  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
-  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
-  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
-  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  static std::once_flag once;                    // handles of several host threads may race to resolve NCCL
+  std::call_once(once, [] {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  });
   return api.ok ? &api : nullptr;
 }
 
@@ -51,6 +54,35 @@ __host__ __device__ inline size_t blob_bytes(size_t per) {
   return per * sizeof(long long) + ((per * sizeof(float) + 7) / 8) * 8;
 }
 
+// merge after the all-gather, straight from the gathered blobs: one CTA per query loads the world * k
+// candidates of its query into shared memory and selects the k best (k <= 32: register lists)
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+merge_gathered_kernel(const unsigned char* __restrict__ blob, int world, int nq, int k,
+                      float* __restrict__ top_s, long long* __restrict__ top_i) {
+  extern __shared__ unsigned char sm_raw[];
+  long long* cid = reinterpret_cast<long long*>(sm_raw);                  // [world * k]
+  long long* wi = cid + (size_t)world * k;                                // [SEL_WARPS * 32]
+  long long* sel_i = wi + SEL_WARPS * 32;                                 // [k]
+  float* csc = reinterpret_cast<float*>(sel_i + k);                       // [world * k]
+  float* ws = csc + (size_t)world * k;                                    // [SEL_WARPS * 32]
+  float* sel_s = ws + SEL_WARPS * 32;                                     // [k]
+  const int q = blockIdx.x;
+  const int per = nq * k, n = world * k;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / k, t = i % k;
+    const unsigned char* base = blob + (size_t)r * blob_bytes(per);
+    cid[i] = reinterpret_cast<const long long*>(base)[q * k + t];
+    csc[i] = reinterpret_cast<const float*>(base + (size_t)per * sizeof(long long))[q * k + t];
+  }
+  __syncthreads();
+  block_select_topk(csc, cid, n, k, ws, wi, sel_s, sel_i);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    top_s[(size_t)q * k + j] = sel_s[j];
+    top_i[(size_t)q * k + j] = sel_i[j];
+  }
+}
+
+// unpack for k > 32 (the general two-stage selection of topk.cu takes contiguous candidate rows)
 __global__ void unpack_gathered_kernel(const unsigned char* __restrict__ blob, int world, int nq,
                                        int k, float* __restrict__ cs, long long* __restrict__ ci) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,30 +124,49 @@ __global__ void place_blocks_kernel(const float* __restrict__ recv, int world, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Peer-memory exchange: merge + all-gather in ONE kernel over NVLink / NVSwitch P2P stores.
+// Peer-memory exchange: local selection + all-gather + merge in ONE kernel over NVLink / NVSwitch P2P stores.
 //
 // Every rank owns an exchange region (cudaMalloc, shared through CUDA IPC):
-//     [2 epochs][world source ranks][cap candidates] x (int64 id, fp32 score)  +  flags [2][world][PEER_MAXQ]
-// Per query q (CTA-strided): the CTA copies this rank's local top-k of q into the slot
-// (epoch, my rank) of EVERY rank's region with plain remote stores, fences at system scope and
-// releases the per-(source rank, query) flag on every rank; it then acquires the `world` flags of q in
-// its own region and merges the world * k candidates (score desc, id asc) straight into the result.
-// No NCCL launch, no unpack pass; the transfer of query q overlaps the merge of the queries before it.
-// Two epochs (call parity) suffice: a rank can only start call n+2 after every peer has pushed call
-// n+1, i.e. after that peer's call-n kernel -- the last reader of the epoch being overwritten -- is
-// complete (stream order).  Waits are bounded: a missing peer traps instead of hanging the GPU.
+//     data  [2 epochs][world source ranks][cap candidates] x (int64 id, fp32 score)
+//     flags [2][world][PEER_MAXQ] u32      meta [2][world] u32 ((nq << 8) | k of the source's call)
+//     ctl   {seq, done, err}               (local use only)
+// Per query q (CTA-strided): the CTA reduces this rank's candidates of q to the local top-k (they may be
+// the k * n_cta per-CTA lists of the fused scan, or already k), copies them into the slot (epoch, my rank)
+// of EVERY rank's region with plain remote stores, fences at system scope and releases the per-(source
+// rank, query) flag on every rank; it then acquires the `world` flags of q in its own region and merges
+// the world * k candidates (score desc, id asc) straight into the result.  No NCCL launch, no unpack
+// pass; the transfer of query q overlaps the merge of the queries before it.
+//
+// The call sequence number lives ON THE DEVICE (ctl.seq, advanced by the last CTA of a launch), so the
+// kernel can be captured in a CUDA graph and replayed, and a host-side early return can never desynchronise
+// the ranks.  Two epochs (sequence parity) suffice: a rank can only start call n+2 after every peer has
+// pushed call n+1, i.e. after that peer's call-n kernel -- the last reader of the epoch being overwritten
+// -- is complete (stream order).
+//
+// Contract (collective): every rank calls with the same nq and k (checked through `meta`; a mismatch is
+// reported like a timeout), on ONE stream per handle.  Progress: a CTA pushes before it waits and grids
+// are identical on all ranks and capped at the co-resident CTA count, so the lowest unfinished query of
+// every rank always has its CTA running.  Waits are bounded by a wall-clock timeout (EVDR_PEER_TIMEOUT_MS,
+// default 30000, 0 = wait forever): on expiry the kernel does NOT trap -- it records the error (device
+// word + pinned host word), writes (-inf, -1) results for the affected queries, skips all further
+// waiting and exits normally; the next evdr_peer_* call on the handle returns EVDR_ERR_STATE.
 // ---------------------------------------------------------------------------------------------
 constexpr int PEER_MAXQ = 4096;           // queries per call
 constexpr int PEER_MAX_WORLD = 16;
-constexpr int PEER_THREADS = 256;
+constexpr int PEER_THREADS = SEL_WARPS * 32;
+
+struct PeerCtl { unsigned seq, done, err, pad; };
 
 __host__ __device__ inline size_t peer_slot_bytes(size_t cap) { return cap * 12; }   // ids then scores
 __host__ __device__ inline size_t peer_data_bytes(int world, size_t cap) {
   return ((2 * (size_t)world * peer_slot_bytes(cap) + 127) / 128) * 128;
 }
-__host__ __device__ inline size_t peer_region_bytes(int world, size_t cap) {
-  return peer_data_bytes(world, cap) + sizeof(unsigned) * 2 * (size_t)world * PEER_MAXQ;
+__host__ __device__ inline size_t peer_flag_bytes(int world) { return sizeof(unsigned) * 2 * (size_t)world * PEER_MAXQ; }
+__host__ __device__ inline size_t peer_meta_off(int world, size_t cap) { return peer_data_bytes(world, cap) + peer_flag_bytes(world); }
+__host__ __device__ inline size_t peer_ctl_off(int world, size_t cap) {
+  return peer_meta_off(world, cap) + ((sizeof(unsigned) * 2 * (size_t)world + 15) / 16) * 16;
 }
+__host__ __device__ inline size_t peer_region_bytes(int world, size_t cap) { return peer_ctl_off(world, cap) + sizeof(PeerCtl); }
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -125,42 +176,93 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+enum { PEER_ERR_TIMEOUT = 1, PEER_ERR_SHAPE = 2 };
 
 __global__ void __launch_bounds__(PEER_THREADS)
 exchange_merge_kernel(unsigned char* const* __restrict__ regions, int world, int rank, int cap,
-                      unsigned seq, const float* __restrict__ loc_s, const long long* __restrict__ loc_i,
-                      int nq, int k, float* __restrict__ top_s, long long* __restrict__ top_i) {
+                      const float* __restrict__ cand_s, const long long* __restrict__ cand_i, int ncand,
+                      int nq, int k, float* __restrict__ top_s, long long* __restrict__ top_i,
+                      unsigned long long timeout_ns, unsigned* __restrict__ err_host) {
   extern __shared__ unsigned char sm_raw[];
-  long long* cid = reinterpret_cast<long long*>(sm_raw);                  // [world * k]
-  float* csc = reinterpret_cast<float*>(cid + (size_t)world * k);         // [world * k]
-  const int epoch = seq & 1u;
+  long long* cid = reinterpret_cast<long long*>(sm_raw);                  // [world * k] gathered candidates
+  long long* wi = cid + (size_t)world * k;                                // [SEL_WARPS * 32] selection scratch
+  long long* loc_i = wi + SEL_WARPS * 32;                                 // [k] this rank's top-k of q
+  float* csc = reinterpret_cast<float*>(loc_i + k);                       // [world * k]
+  float* ws = csc + (size_t)world * k;                                    // [SEL_WARPS * 32]
+  float* loc_s = ws + SEL_WARPS * 32;                                     // [k]
   const size_t slot = peer_slot_bytes(cap);
   const size_t data = peer_data_bytes(world, cap);
+  PeerCtl* ctl = reinterpret_cast<PeerCtl*>(regions[rank] + peer_ctl_off(world, cap));
+  const unsigned seq = *reinterpret_cast<volatile unsigned*>(&ctl->seq) + 1u;   // same for every CTA of the launch
+  const int epoch = seq & 1u;
+  const unsigned meta_mine = ((unsigned)nq << 8) | (unsigned)k;
   const int per = nq * k;
   const int n = world * k;
   for (int q = blockIdx.x; q < nq; q += gridDim.x) {
-    // ---- push: this rank's k candidates of query q into slot (epoch, rank) of every region
-    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+    // ---- this rank's k best of query q
+    if (ncand > k) {
+      block_select_topk(cand_s + (size_t)q * ncand, cand_i + (size_t)q * ncand, ncand, k, ws, wi, loc_s, loc_i);
+    } else {
+      for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        loc_s[t] = cand_s[(size_t)q * k + t];
+        loc_i[t] = cand_i[(size_t)q * k + t];
+      }
+      __syncthreads();
+    }
+    // ---- push them into slot (epoch, rank) of every region
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int r = i / k, t = i % k;
       unsigned char* base = regions[r] + ((size_t)epoch * world + rank) * slot;
-      reinterpret_cast<long long*>(base)[q * k + t] = loc_i[(size_t)q * k + t];
-      reinterpret_cast<float*>(base + (size_t)per * 8)[q * k + t] = loc_s[(size_t)q * k + t];
+      reinterpret_cast<long long*>(base)[q * k + t] = loc_i[t];
+      reinterpret_cast<float*>(base + (size_t)per * 8)[q * k + t] = loc_s[t];
     }
     __threadfence_system();
     __syncthreads();
+    bool ok = true;
     if (threadIdx.x < world) {
-      unsigned* fl = reinterpret_cast<unsigned*>(regions[threadIdx.x] + data);
-      st_release_sys(fl + ((size_t)epoch * world + rank) * PEER_MAXQ + q, seq);
+      unsigned char* peer = regions[threadIdx.x];
+      reinterpret_cast<unsigned*>(peer + peer_meta_off(world, cap))[epoch * world + rank] = meta_mine;
+      st_release_sys(reinterpret_cast<unsigned*>(peer + data) + ((size_t)epoch * world + rank) * PEER_MAXQ + q, seq);
       // ---- wait for source rank threadIdx.x to have delivered query q here
       const unsigned* mine = reinterpret_cast<const unsigned*>(regions[rank] + data) +
                              ((size_t)epoch * world + threadIdx.x) * PEER_MAXQ + q;
-      unsigned spins = 0;
+      volatile unsigned* derr = &ctl->err;
+      unsigned long long t0 = 0;
       while (ld_acquire_sys(mine) != seq) {
-        __nanosleep(256);
-        if (++spins > (1u << 25)) __trap();        // ~30 s: a peer never arrived
+        if (*derr != 0u) { ok = false; break; }            // a wait already failed in this launch
+        if (t0 == 0) t0 = global_timer_ns();
+        __nanosleep(200);
+        if (timeout_ns != 0 && global_timer_ns() - t0 > timeout_ns) {
+          atomicCAS(&ctl->err, 0u, (unsigned)PEER_ERR_TIMEOUT | ((unsigned)threadIdx.x << 8));
+          *reinterpret_cast<volatile unsigned*>(err_host) = (unsigned)PEER_ERR_TIMEOUT | ((unsigned)threadIdx.x << 8);
+          ok = false;
+          break;
+        }
+      }
+      if (ok) {
+        const unsigned m = __ldcv(reinterpret_cast<const unsigned*>(regions[rank] + peer_meta_off(world, cap)) +
+                                  epoch * world + threadIdx.x);
+        if (m != meta_mine) {                                // the peer called with another nq / k
+          atomicCAS(&ctl->err, 0u, (unsigned)PEER_ERR_SHAPE | ((unsigned)threadIdx.x << 8));
+          *reinterpret_cast<volatile unsigned*>(err_host) = (unsigned)PEER_ERR_SHAPE | ((unsigned)threadIdx.x << 8);
+          ok = false;
+        }
       }
     }
-    __syncthreads();
+    if (!__syncthreads_and(ok ? 1 : 0)) {
+      for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        top_s[(size_t)q * k + t] = -INFINITY;
+        top_i[(size_t)q * k + t] = -1;
+      }
+      __syncthreads();
+      continue;
+    }
     // ---- gather the world * k candidates of q (remote writes: bypass L1)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int r = i / k, t = i % k;
@@ -190,6 +292,101 @@ exchange_merge_kernel(unsigned char* const* __restrict__ regions, int world, int
     }
     __syncthreads();
   }
+  // ---- the last CTA of the launch advances the call sequence number
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl->done, 1u) == gridDim.x - 1) {
+      ctl->done = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(&ctl->seq) = seq;
+    }
+  }
+}
+
+static size_t exchange_smem(int world, int k) {
+  return ((size_t)world * k + SEL_WARPS * 32 + k) * (sizeof(long long) + sizeof(float));
+}
+
+// candidates (nq, ncand) of this rank -> global top-k on every rank (collective); ncand == k or k <= 32
+int peer_exchange(evdr_handle* h, const float* cand_s, const long long* cand_i, int nq, int ncand, int k,
+                  float* top_scores, long long* top_ids, cudaStream_t st) {
+  if (!h->peer_ptrs_dev) return set_error(EVDR_ERR_STATE, "peer exchange before evdr_peer_connect");
+  EVDR_CHECK_ARG(nq >= 1 && nq <= PEER_MAXQ && k >= 1 && k <= 255 && (long long)nq * k <= h->peer_cap,
+                 "peer exchange: nq=%d x k=%d exceeds the exchange region (%d candidates, %d queries)",
+                 nq, k, h->peer_cap, PEER_MAXQ);
+  EVDR_CHECK_ARG(ncand == k || (ncand > k && k <= 32), "peer exchange: %d candidates per query need k <= 32", ncand);
+  if (h->peer_err_host && *reinterpret_cast<volatile unsigned*>(h->peer_err_host) != 0u) {
+    const unsigned e = *reinterpret_cast<volatile unsigned*>(h->peer_err_host);
+    return set_error(EVDR_ERR_STATE, "peer exchange is disabled on this handle: an earlier call %s (rank %u)",
+                     (e & 0xffu) == PEER_ERR_TIMEOUT ? "timed out waiting for a peer" : "met a peer with another nq / k",
+                     e >> 8);
+  }
+  const size_t smem = exchange_smem(h->peer_world, k);
+  if (smem > 48 * 1024) {
+    if (smem > h->smem_optin) return set_error(EVDR_ERR_UNSUPPORTED, "peer exchange: world * k too large for shared memory");
+    EVDR_CUDA(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  // identical on every rank (same binary, same device type) and never more than can be co-resident
+  int per_sm = 0;
+  EVDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_merge_kernel, PEER_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  const int grid = nq < per_sm * h->sm_count ? nq : per_sm * h->sm_count;
+  exchange_merge_kernel<<<grid, PEER_THREADS, smem, st>>>(
+      h->peer_ptrs_dev, h->peer_world, h->peer_rank, h->peer_cap, cand_s, cand_i, ncand, nq, k, top_scores,
+      top_ids, h->peer_timeout_ns, h->peer_err_dev);
+  EVDR_LAUNCH_CHECK("exchange_merge_kernel");
+  return EVDR_OK;
+}
+
+// candidates of this rank -> global top-k through ONE ncclAllGather; `fill(loc_s, loc_i)` writes this
+// rank's nq * k (score, id) pairs straight into the send blob
+template <typename Fill>
+static int nccl_exchange(evdr_handle* h, int nq, int k, float* top_scores, long long* top_ids, cudaStream_t st,
+                         Fill fill) {
+  if (!h->nccl_comm) return set_error(EVDR_ERR_STATE, "sharded search before evdr_comm_init");
+  NcclApi* api = nccl_api();
+  if (!api) return set_error(EVDR_ERR_NCCL, "libnccl.so.2 not loadable");
+  const int world = h->world;
+  const size_t per = (size_t)nq * k;
+  const size_t rank_bytes = blob_bytes(per);
+  // stream-ordered scratch: [send blob][recv blobs x world][cand ids world*per][cand scores world*per]
+  unsigned char* ws = nullptr;
+  EVDR_CUDA(ws_alloc(h, &ws, rank_bytes * (2 * (size_t)world + 1) + 64, st));
+  unsigned char* send = ws;
+  unsigned char* recv = ws + rank_bytes;
+  long long* loc_i = reinterpret_cast<long long*>(send);
+  float* loc_s = reinterpret_cast<float*>(send + per * sizeof(long long));
+  int rc = fill(loc_s, loc_i);
+  if (rc != EVDR_OK) { cudaFreeAsync(ws, st); return rc; }
+  nccl_result_t r = api->AllGather(send, recv, rank_bytes, kNcclChar, static_cast<nccl_comm_t>(h->nccl_comm), st);
+  if (r != 0) {
+    cudaFreeAsync(ws, st);
+    return set_error(EVDR_ERR_NCCL, "ncclAllGather failed: %s", api->GetErrorString(r));
+  }
+  if (k <= 32) {
+    const size_t smem = exchange_smem(world, k);
+    merge_gathered_kernel<<<nq, SEL_WARPS * 32, smem, st>>>(recv, world, nq, k, top_scores, top_ids);
+    cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(ws, st);
+    if (le != cudaSuccess)
+      return set_error(EVDR_ERR_CUDA, "launch of merge_gathered_kernel failed: %s", cudaGetErrorString(le));
+    return EVDR_OK;
+  }
+  long long* cand_i = reinterpret_cast<long long*>(recv + rank_bytes * world);
+  float* cand_s = reinterpret_cast<float*>(cand_i + (size_t)world * per);
+  const int total = world * (int)per;
+  unpack_gathered_kernel<<<(total + 255) / 256, 256, 0, st>>>(recv, world, nq, k, cand_s, cand_i);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    cudaFreeAsync(ws, st);
+    return set_error(EVDR_ERR_CUDA, "launch of unpack_gathered_kernel failed: %s", cudaGetErrorString(le));
+  }
+  rc = evdr_topk_merge(h, cand_s, reinterpret_cast<const int64_t*>(cand_i), nq, world * k, k, top_scores,
+                       reinterpret_cast<int64_t*>(top_ids), st);
+  cudaFreeAsync(ws, st);
+  return rc;
 }
 
 }  // namespace evdr
@@ -215,12 +412,24 @@ int evdr_peer_region_init(evdr_handle* h, int rank, int world, int max_candidate
     cudaFree(reg);
     return set_error(EVDR_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
   }
+  // error word: pinned + mapped, so the host sees a failed wait without synchronising
+  e = cudaHostAlloc(reinterpret_cast<void**>(&h->peer_err_host), sizeof(unsigned), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *h->peer_err_host = 0u;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->peer_err_dev), h->peer_err_host, 0);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(reg);
+    return set_error(EVDR_ERR_CUDA, "mapped error word for the peer exchange: %s", cudaGetErrorString(e));
+  }
+  unsigned long long ms = 30000ull;
+  if (const char* t = getenv("EVDR_PEER_TIMEOUT_MS")) ms = strtoull(t, nullptr, 10);
+  h->peer_timeout_ns = ms * 1000000ull;
   memcpy(ipc_handle_out, &ipc, sizeof(ipc));
   h->peer_local = reg;
   h->peer_rank = rank;
   h->peer_world = world;
   h->peer_cap = max_candidates;
-  h->peer_seq = 0;
   return EVDR_OK;
 }
 
@@ -260,22 +469,15 @@ int evdr_peer_sharded_topk(evdr_handle* h, const float* local_scores, int64_t ld
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t per = (size_t)nq * k;
   unsigned char* ws = nullptr;
-  EVDR_CUDA(cudaMallocAsync(&ws, per * 12 + 64, st));
+  EVDR_CUDA(ws_alloc(h, &ws, per * 12 + 64, st));
   int64_t* loc_i = reinterpret_cast<int64_t*>(ws);
   float* loc_s = reinterpret_cast<float*>(ws + per * 8);
   int rc = evdr_topk(h, local_scores, ld, nq, np_local, k, nullptr, id_offset, loc_s, loc_i, stream);
-  if (rc != EVDR_OK) { cudaFreeAsync(ws, st); return rc; }
-  const unsigned seq = ++h->peer_seq;
-  const int grid = nq < 2 * h->sm_count ? nq : 2 * h->sm_count;
-  const size_t smem = (size_t)h->peer_world * k * 12;
-  exchange_merge_kernel<<<grid, PEER_THREADS, smem, st>>>(
-      h->peer_ptrs_dev, h->peer_world, h->peer_rank, h->peer_cap, seq, loc_s,
-      reinterpret_cast<const long long*>(loc_i), nq, k, top_scores, reinterpret_cast<long long*>(top_ids));
-  cudaError_t le = cudaGetLastError();
+  if (rc == EVDR_OK)
+    rc = peer_exchange(h, loc_s, reinterpret_cast<const long long*>(loc_i), nq, k, k, top_scores,
+                       reinterpret_cast<long long*>(top_ids), st);
   cudaFreeAsync(ws, st);
-  if (le != cudaSuccess)
-    return set_error(EVDR_ERR_CUDA, "launch of exchange_merge_kernel failed: %s", cudaGetErrorString(le));
-  return EVDR_OK;
+  return rc;
 }
 
 int evdr_allgather_score_rows(evdr_handle* h, const float* local_scores, int64_t ld, int B, int np_total,
@@ -297,7 +499,7 @@ int evdr_allgather_score_rows(evdr_handle* h, const float* local_scores, int64_t
   const int cmax = part_count(np_total, world, 0);
   const size_t blk = (size_t)B * cmax;
   float* ws = nullptr;
-  EVDR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), sizeof(float) * blk * ((size_t)world + 1), st));
+  EVDR_CUDA(evdr::ws_alloc(h, reinterpret_cast<void**>(&ws), sizeof(float) * blk * ((size_t)world + 1), st));
   float* send = ws;
   float* recv = ws + blk;
   pad_block_kernel<<<(unsigned)((blk + 255) / 256), 256, 0, st>>>(local_scores, ld, B, cnt, cmax, send);
@@ -322,6 +524,8 @@ int evdr_destroy(evdr_handle* h) {
     if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_opened[r]);
   if (h->peer_ptrs_dev) cudaFree(h->peer_ptrs_dev);
   if (h->peer_local) cudaFree(h->peer_local);
+  if (h->peer_err_host) cudaFreeHost(h->peer_err_host);
+  if (h->pool) cudaMemPoolDestroy(h->pool);
   if (h->nccl_comm) {
     NcclApi* api = nccl_api();
     if (api) api->CommDestroy(static_cast<nccl_comm_t>(h->nccl_comm));
@@ -368,35 +572,60 @@ int evdr_sharded_topk(evdr_handle* h, const float* local_scores, int64_t ld, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (h->world == 1 && !h->nccl_comm)
     return evdr_topk(h, local_scores, ld, nq, np_local, k, nullptr, id_offset, top_scores, top_ids, stream);
-  if (!h->nccl_comm) return set_error(EVDR_ERR_STATE, "evdr_sharded_topk before evdr_comm_init");
-  NcclApi* api = nccl_api();
-  if (!api) return set_error(EVDR_ERR_NCCL, "libnccl.so.2 not loadable");
-  const int world = h->world;
-  const size_t per = (size_t)nq * k;
-  const size_t rank_bytes = blob_bytes(per);
-  // stream-ordered scratch: [send blob][recv blobs x world][cand ids world*per][cand scores world*per]
+  return nccl_exchange(h, nq, k, top_scores, reinterpret_cast<long long*>(top_ids), st,
+                       [&](float* loc_s, long long* loc_i) {
+                         return evdr_topk(h, local_scores, ld, nq, np_local, k, nullptr, id_offset, loc_s,
+                                          reinterpret_cast<int64_t*>(loc_i), stream);
+                       });
+}
+
+/* Fused search: packed queries -> local scan with the top-k folded into the scan's epilogue (when the launch
+ * has one query group; otherwise scores + evdr_topk on a stream-ordered scratch row) -> candidate exchange
+ * (exchange: 0 = none / single GPU, 1 = ncclAllGather + merge, 2 = peer-memory kernel) -> global top-k. */
+int evdr_sharded_search(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq, const void* tokens,
+                        int64_t n_tokens, const int32_t* chunk_off, int np, int64_t total_chunks, int k,
+                        int64_t id_offset, int exchange, float* top_scores, int64_t* top_ids, void* stream) {
+  EVDR_REQUIRE_HANDLE(h);
+  EVDR_CHECK_ARG(top_scores && top_ids, "evdr_sharded_search: null output pointer");
+  EVDR_CHECK_ARG(exchange >= 0 && exchange <= 2, "evdr_sharded_search: exchange=%d (0 none, 1 nccl, 2 peer)", exchange);
+  EVDR_CHECK_ARG(k >= 1 && k <= 128, "evdr_sharded_search: k=%d outside [1,128]", k);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool solo = exchange == 0 || (exchange == 1 && h->world == 1 && !h->nccl_comm);
+  // per-CTA candidate lists of the fused scan (k <= 32) ...
+  const int max_cta = h->sm_count;
   unsigned char* ws = nullptr;
-  EVDR_CUDA(cudaMallocAsync(&ws, rank_bytes * (2 * (size_t)world + 1) + 64, st));
-  unsigned char* send = ws;
-  unsigned char* recv = ws + rank_bytes;
-  long long* cand_i = reinterpret_cast<long long*>(recv + rank_bytes * world);
-  float* cand_s = reinterpret_cast<float*>(cand_i + (size_t)world * per);
-  int64_t* loc_i = reinterpret_cast<int64_t*>(send);
-  float* loc_s = reinterpret_cast<float*>(send + per * sizeof(long long));
-  int rc = evdr_topk(h, local_scores, ld, nq, np_local, k, nullptr, id_offset, loc_s, loc_i, stream);
-  if (rc != EVDR_OK) { cudaFreeAsync(ws, st); return rc; }
-  nccl_result_t r = api->AllGather(send, recv, rank_bytes, kNcclChar,
-                                   static_cast<nccl_comm_t>(h->nccl_comm), st);
-  if (r != 0) {
+  const size_t cand_n = (size_t)nq * max_cta * (k <= 32 ? k : 0);
+  const size_t row_bytes = sizeof(float) * (size_t)nq * np;     // ... or the score rows of the unfused route
+  EVDR_CUDA(ws_alloc(h, &ws, cand_n * 12 + 64, st));
+  long long* cand_i = reinterpret_cast<long long*>(ws);
+  float* cand_s = reinterpret_cast<float*>(ws + cand_n * 8);
+  int n_cta = 0;
+  int rc = k <= 32 ? scan_topk(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, k, id_offset,
+                               cand_s, cand_i, &n_cta, st)
+                   : EVDR_ERR_UNSUPPORTED;
+  if (rc == EVDR_OK) {
+    const int ncand = n_cta * k;
+    if (solo) rc = select_candidates(h, cand_s, cand_i, nq, ncand, k, top_scores, reinterpret_cast<long long*>(top_ids), st);
+    else if (exchange == 2) rc = peer_exchange(h, cand_s, cand_i, nq, ncand, k, top_scores, reinterpret_cast<long long*>(top_ids), st);
+    else rc = nccl_exchange(h, nq, k, top_scores, reinterpret_cast<long long*>(top_ids), st,
+                            [&](float* loc_s, long long* loc_i) {
+                              return select_candidates(h, cand_s, cand_i, nq, ncand, k, loc_s, loc_i, st);
+                            });
     cudaFreeAsync(ws, st);
-    return set_error(EVDR_ERR_NCCL, "ncclAllGather failed: %s", api->GetErrorString(r));
+    return rc;
   }
-  const int total = world * (int)per;
-  unpack_gathered_kernel<<<(total + 255) / 256, 256, 0, st>>>(recv, world, nq, k, cand_s, cand_i);
-  EVDR_LAUNCH_CHECK("unpack_gathered_kernel");
-  rc = evdr_topk_merge(h, cand_s, reinterpret_cast<const int64_t*>(cand_i), nq, world * k, k,
-                       top_scores, top_ids, stream);
   cudaFreeAsync(ws, st);
+  if (rc != EVDR_ERR_UNSUPPORTED) return rc;
+  // several query groups (more than 8 queries), short pages or k > 32: scores, then the two-stage top-k
+  float* rows = nullptr;
+  EVDR_CUDA(ws_alloc(h, &rows, row_bytes, st));
+  rc = evdr_maxsim_packed_fwd(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, 0, 1, rows, np, stream);
+  if (rc == EVDR_OK) {
+    if (solo) rc = evdr_topk(h, rows, np, nq, np, k, nullptr, id_offset, top_scores, top_ids, stream);
+    else if (exchange == 2) rc = evdr_peer_sharded_topk(h, rows, np, nq, np, k, id_offset, top_scores, top_ids, stream);
+    else rc = evdr_sharded_topk(h, rows, np, nq, np, k, id_offset, top_scores, top_ids, stream);
+  }
+  cudaFreeAsync(rows, st);
   return rc;
 }
 

@@ -9,6 +9,7 @@
 // given (host passes the rank of the docid string in descending order = trec_eval's
 // rule) else the column index / candidate id.
 #include "common.cuh"
+#include "topk_dev.cuh"
 
 namespace evdr {
 
@@ -405,7 +406,7 @@ static int run_topk(evdr_handle* h, const float* scores, long long ld, int nq, i
   }
   const size_t per = (size_t)nq * nsplit * k;
   unsigned char* ws = nullptr;
-  EVDR_CUDA(cudaMallocAsync(&ws, per * (sizeof(float) + 2 * sizeof(long long)), st));
+  EVDR_CUDA(evdr::ws_alloc(h, &ws, per * (sizeof(float) + 2 * sizeof(long long)), st));
   long long* p_tie = reinterpret_cast<long long*>(ws);
   long long* p_id = p_tie + per;
   float* p_s = reinterpret_cast<float*>(p_id + per);
@@ -425,6 +426,30 @@ static int run_topk(evdr_handle* h, const float* scores, long long ld, int nq, i
     EVDR_LAUNCH_CHECK("topk_select_kernel(stage2)");
   }
   EVDR_CUDA(cudaFreeAsync(ws, st));
+  return EVDR_OK;
+}
+
+// k <= 32 best of explicit candidate rows: one CTA per query, register lists per warp + rank merge
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+select_candidates_kernel(const float* __restrict__ cand_s, const long long* __restrict__ cand_i, int ncand, int k,
+                         float* __restrict__ top_s, long long* __restrict__ top_i) {
+  __shared__ float ws[SEL_WARPS * 32], sel_s[32];
+  __shared__ long long wi[SEL_WARPS * 32], sel_i[32];
+  const int q = blockIdx.x;
+  block_select_topk(cand_s + (size_t)q * ncand, cand_i + (size_t)q * ncand, ncand, k, ws, wi, sel_s, sel_i);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    top_s[(size_t)q * k + j] = sel_s[j];
+    top_i[(size_t)q * k + j] = sel_i[j];
+  }
+}
+
+int select_candidates(evdr_handle* h, const float* cand_s, const long long* cand_i, int nq, int ncand, int k,
+                      float* top_s, long long* top_i, cudaStream_t st) {
+  (void)h;
+  EVDR_CHECK_ARG(cand_s && cand_i && top_s && top_i && nq >= 1 && ncand >= 1 && k >= 1 && k <= 32,
+                 "select_candidates: bad arguments (k=%d must be <= 32)", k);
+  select_candidates_kernel<<<nq, SEL_WARPS * 32, 0, st>>>(cand_s, cand_i, ncand, k, top_s, top_i);
+  EVDR_LAUNCH_CHECK("select_candidates_kernel");
   return EVDR_OK;
 }
 

@@ -44,7 +44,7 @@ extern "C" int evdr_maxsim_train_fwd(evdr_handle* h, const void* Q, int q_dtype,
   const size_t b_r = align256(rowmax_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned char* ws = nullptr;
-  EVDR_CUDA(cudaMallocAsync(&ws, b_q + b_m + b_o + b_t + b_r, st));
+  EVDR_CUDA(evdr::ws_alloc(h, &ws, b_q + b_m + b_o + b_t + b_r, st));
   unsigned char* Qb = ws;
   uint8_t* qm32 = ws + b_q;
   int32_t* chunk_off = reinterpret_cast<int32_t*>(ws + b_q + b_m);

@@ -144,6 +144,79 @@ class ShardedSearch:
         return self._merge(torch.cat(gs, dim=1), torch.cat(gi, dim=1), k)
 
 
+    # ------------------------------------------------------------------ fused search
+    _EXCHANGE = {"none": 0, "nccl": 1, "peer": 2}
+
+    def search_packed(self, pk, Qb: torch.Tensor, qm32: torch.Tensor, k: int,
+                      out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """Packed queries against this rank's shard `pk` -> global top-k on every rank in ONE library call
+        (evdr_sharded_search): local scan with the top-k folded into its epilogue (<= 8 queries on long pages:
+        only k candidates per CTA leave the SM, no (nq, np) score row), candidate exchange, merge."""
+        if pk.k_blocks != 1:
+            raise NotImplementedError("fused search runs on plain bf16 shards")
+        if pk.n_pages != self.end - self.start:
+            raise ValueError("shard does not match this rank's page range")
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        mode = self.mode if world > 1 or self.mode == "peer" else "none"
+        if mode not in self._EXCHANGE:
+            raise ValueError(f"search_packed needs mode 'nccl' or 'peer', not {self.mode!r}")
+        nq = Qb.shape[0]
+        dev = pk.device
+        top_s, top_i = out if out is not None else (torch.empty((nq, k), dtype=torch.float32, device=dev),
+                                                     torch.empty((nq, k), dtype=torch.int64, device=dev))
+        lib = _lib.load()
+        _lib.check(lib.evdr_sharded_search(_lib.handle(dev), Qb.data_ptr(), qm32.data_ptr(), nq, pk.tokens.data_ptr(),
+                                           pk.tokens.shape[0], pk.chunk_off.data_ptr(), pk.n_pages, pk.total_chunks,
+                                           k, self.start, self._EXCHANGE[mode], top_s.data_ptr(), top_i.data_ptr(),
+                                           _lib.stream_ptr(dev)), "evdr_sharded_search")
+        return top_s, top_i
+
+    def search(self, pk, Q: torch.Tensor, qmask: torch.Tensor, k: int):
+        """(nq, lq <= 32, 128) queries -> global top-k (scores (nq, k), ids (nq, k) int64) on every rank."""
+        from .corpus import pack_queries
+        if Q.shape[1] > _lib.TC_LQ:
+            return self.topk(pk.score(Q, qmask), k)            # long queries: 32-token groups, unfused
+        Qb, qm32 = pack_queries(Q, qmask)
+        return self.search_packed(pk, Qb, qm32, k)
+
+
+class GraphedSearch:
+    """pack -> scan (+ fused top-k) -> exchange -> merge captured ONCE as a CUDA graph and replayed per query
+    batch: the latency path of a sharded corpus (1 M pages over 8 GPUs: a 4.5 ms scan, where four launches
+    and their host-side issue would otherwise show).  Inputs are copied into static buffers, results are
+    returned in static buffers (valid until the next call).  Collective at world > 1: every rank replays."""
+
+    def __init__(self, search: "ShardedSearch", pk, nq: int, k: int = 10, lq: int = _lib.TC_LQ):
+        from .corpus import pack_queries
+        dev = pk.device
+        self.search, self.pk, self.k = search, pk, k
+        self.Q = torch.zeros((nq, lq, _lib.TC_DIM), dtype=torch.float32, device=dev)
+        self.qmask = torch.zeros((nq, lq), dtype=torch.bool, device=dev)
+        self.top_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        self.top_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+
+        def body():
+            Qb, qm32 = pack_queries(self.Q, self.qmask)
+            search.search_packed(pk, Qb, qm32, k, out=(self.top_s, self.top_i))
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                    # warm-up outside capture (lazy module loads, pool growth)
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def __call__(self, Q: torch.Tensor, qmask: torch.Tensor):
+        self.Q.copy_(Q, non_blocking=True)
+        self.qmask.copy_(qmask, non_blocking=True)
+        self.graph.replay()
+        return self.top_s, self.top_i
+
+
 class _GatherScoreRows(torch.autograd.Function):
     """(B, n_local) score block of this rank's pages -> full (B, n_total) rows on every rank; the backward
     is the local column slice of the incoming gradient (each rank owns its pages' parameters: no reduce)."""

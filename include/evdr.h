@@ -64,7 +64,9 @@ EVDR_API const char* evdr_last_error(void);
 
 /* Handle: per (thread, device); holds the device ordinal, SM count, the driver
  * entry point used to encode TMA descriptors and, after evdr_comm_init, the NCCL
- * communicator.  Not thread-safe. */
+ * communicator.  A handle is single-threaded: one host thread (and, for the peer exchange, one
+ * stream) at a time.  Stream-ordered scratch comes from a memory pool owned by the handle
+ * (release threshold 2 GiB, EVDR_POOL_KEEP_MB); the device's default pool is not touched. */
 EVDR_API int evdr_create(int device, evdr_handle** out);
 EVDR_API int evdr_destroy(evdr_handle* h);
 EVDR_API int evdr_sm_count(const evdr_handle* h);
@@ -281,15 +283,21 @@ EVDR_API int evdr_allgather_score_rows(evdr_handle* h, const float* local_scores
                                        int np_total, float* out_dev, int64_t out_ld, void* stream);
 
 /* Peer-memory exchange (no NCCL on the data path): every rank owns an exchange region shared through
- * CUDA IPC; ONE kernel copies the local top-k of each query into all peers' regions with remote
- * stores over NVLink, releases per-query flags, acquires the peers' flags and merges the world * k
- * candidates into the result (same order as evdr_topk_merge: score descending, id ascending).
+ * CUDA IPC; ONE kernel reduces the local candidates of each query to the local top-k, copies them into
+ * all peers' regions with remote stores over NVLink, releases per-query flags, acquires the peers' flags
+ * and merges the world * k candidates into the result (same order as evdr_topk_merge: score descending,
+ * id ascending).
  *   evdr_peer_region_init : allocate this rank's region for up to `max_candidates` = nq * k entries per
  *                           call and return its 64-byte cudaIpcMemHandle_t;
  *   evdr_peer_connect     : `all_ipc_handles` = world x 64 bytes in rank order (the host plumbing --
  *                           torch.distributed -- gathers them); opens every peer's region;
  *   evdr_peer_sharded_topk: collective, same arguments and result as evdr_sharded_topk.  nq <= 4096.
- * Waits are bounded (~30 s): a rank that never arrives traps the kernel instead of hanging the GPU. */
+ * Contract: every rank makes the same calls with the same nq and k (checked on the device), on one
+ * stream per handle.  The call sequence number lives on the device, so the kernel may be captured in a
+ * CUDA graph.  Waits are bounded by EVDR_PEER_TIMEOUT_MS (default 30000; 0 = wait forever like NCCL): when
+ * a peer never arrives (or arrives with another nq / k) the kernel does not trap -- the affected queries
+ * get (-inf, -1) results, the launch completes, and every later evdr_peer_* / peer-mode search call on
+ * the handle returns EVDR_ERR_STATE (the process stays alive and can fall back to the NCCL exchange). */
 #define EVDR_IPC_HANDLE_BYTES 64
 EVDR_API int evdr_peer_region_init(evdr_handle* h, int rank, int world, int max_candidates,
                                    void* ipc_handle_out_64B);
@@ -298,6 +306,21 @@ EVDR_API int evdr_peer_world(const evdr_handle* h);
 EVDR_API int evdr_peer_sharded_topk(evdr_handle* h, const float* local_scores_dev, int64_t ld,
                                     int nq, int np_local, int k, int64_t id_offset,
                                     float* top_scores_dev, int64_t* top_ids_dev, void* stream);
+
+/* Fused search (A1 + A7 + the exchange in one library call; mainv2_iter_listwise.py:309-320 at retrieval
+ * scale): packed queries -> local scan -> local top-k -> candidate exchange -> global top-k on every rank.
+ * With at most 8 queries on long pages (one query group) and k <= 32 the top-k is folded into the scan's
+ * epilogue: every epilogue warp keeps the k best (score, page) of its query in registers and only
+ * k candidates per (query, CTA) leave the SM -- the (nq, np) score row is never written; other shapes
+ * score into a stream-ordered scratch row and run evdr_topk.  Results are identical either way.
+ *   exchange: 0 = none (single GPU), 1 = ncclAllGather + merge (needs evdr_comm_init),
+ *             2 = peer-memory kernel (needs evdr_peer_connect).
+ * ids are page + id_offset; slots beyond np are (-inf, -1).  All launches go to `stream`; the sequence is
+ * CUDA-graph capturable. */
+EVDR_API int evdr_sharded_search(evdr_handle* h, const void* Qb_dev, const uint8_t* qmask32_dev, int nq,
+                                 const void* tokens_dev, int64_t n_tokens, const int32_t* chunk_off_dev,
+                                 int np, int64_t total_chunks, int k, int64_t id_offset, int exchange,
+                                 float* top_scores_dev, int64_t* top_ids_dev, void* stream);
 
 /* ------------------------------------------------------------------------
  * A4  fused mask * l2_normalize (utils/preprocess_data.py:8-9 applied as

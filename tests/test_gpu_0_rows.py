@@ -179,6 +179,48 @@ def test_A7_topk_and_trec_measures(evdr, cuda):
     assert got["mRR"]["MRR@10"] == want["mRR"]["MRR@10"]      # divides by len(qrels) like mteb / BEIR
 
 
+@pytest.mark.parametrize("nq", [1, 4, 5, 8, 13])
+def test_A7_topk_fused_into_the_scan(evdr, cuda, nq):
+    """north_star: 'a fused warp-level top-k'.  With <= 8 queries the scan keeps the k best pages per query in
+    registers and only k candidates per CTA leave the SM (evdr_sharded_search): ids and scores bit-identical to
+    evdr_topk / torch.topk over the full score row of the unfused scan (13 queries: the unfused route)."""
+    toks = evdr.synth.make_uniform_corpus(3000, 1040, device=cuda, seed=31)
+    toks[1500:1510] = toks[7:17]                               # duplicated pages: exact score ties, id order decides
+    pm = torch.ones(3000, 1040, dtype=torch.bool, device=cuda)
+    Q, qm, rel = evdr.synth.make_queries(toks, pm, nq, 32, seed=32, sigma=2.0, min_len=8, drop=0.1)
+    pk = evdr.PackedPages.from_uniform_tokens(toks, page_offset=7000)
+    full = pk.score(Q, qm)
+    for k in (1, 10, 32):
+        want_s, want_i = evdr.top_k(full, k, id_offset=7000)
+        got_s, got_i = pk.search(Q, qm, k)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s), (nq, k)
+        ts, ti = torch.topk(full, k, dim=1)
+        assert torch.equal(got_s, ts)
+    # ragged pages, a corpus smaller than the grid, k beyond the page count
+    P, pmask = evdr.synth.make_pages(37, 700, seed=5, device=cuda, n_holes=4, empty_frac=0.05, min_len=100)
+    Qs, qms, _ = evdr.synth.make_queries(P, pmask, min(nq, 4), 32, seed=6, sigma=2.0)
+    pks = evdr.PackedPages.from_padded(P, pmask, varlen=True)
+    want_s, want_i = evdr.top_k(pks.score(Qs, qms), 32)
+    got_s, got_i = pks.search(Qs, qms, 32)
+    assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+    small = evdr.PackedPages.from_padded(P[:5], pmask[:5], varlen=True)
+    got_s, got_i = small.search(Qs, qms, 10)
+    assert (got_i[:, 5:] == -1).all() and torch.isinf(got_s[:, 5:]).all()
+
+
+def test_A7_graphed_search_replays(evdr, cuda):
+    """pack -> scan + top-k -> merge captured once as a CUDA graph: every replay equals the eager search."""
+    toks = evdr.synth.make_uniform_corpus(2500, 1040, device=cuda, seed=41)
+    pm = torch.ones(2500, 1040, dtype=torch.bool, device=cuda)
+    pk = evdr.PackedPages.from_uniform_tokens(toks)
+    gs = evdr.GraphedSearch(evdr.ShardedSearch((0, 2500), mode="nccl"), pk, 1, 10)
+    for seed in range(4):
+        Q, qm, _ = evdr.synth.make_queries(toks, pm, 1, 32, seed=50 + seed, sigma=2.0, min_len=8)
+        want_s, want_i = evdr.top_k(pk.score(Q, qm), 10)
+        got_s, got_i = gs(Q.float(), qm)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+
+
 # --------------------------------------------------------------------------------------- A8
 def test_A8_rank_gap_and_hard_token_mining(evdr, cuda):
     z = np.load(U.GOLDEN / "losses.npz")

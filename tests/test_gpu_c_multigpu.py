@@ -50,6 +50,26 @@ def _worker(rank, world, port, ret):
         ok = ok and torch.equal(pi, ni) and torch.equal(ps, ns)
         ps, pi = peer.topk(local[:1], 3)
         ok = ok and torch.equal(pi, top_i[:1, :3])
+        # fused search (scan with the top-k in its epilogue + exchange in one library call) on uniform
+        # 1040-slot pages: 1, 3 and 7 queries take the fused route, 21 the scores + top-k route; both
+        # exchange modes; bit-identical to the single-GPU top-k of the full score rows; graph replay too
+        toks = evdr.synth.make_uniform_corpus(2001, 1040, device=dev, seed=77)          # same on every rank
+        pmu = torch.ones(2001, 1040, dtype=torch.bool, device=dev)
+        ulo, uhi = evdr.partition_pages(2001, world)[rank]
+        ushard = evdr.PackedPages.from_uniform_tokens(toks[ulo:uhi].contiguous(), page_offset=ulo)
+        whole = evdr.PackedPages.from_uniform_tokens(toks)
+        for nq_f in (1, 3, 7, 21):
+            Qf, qmf, _ = evdr.synth.make_queries(toks, pmu, nq_f, 32, seed=90 + nq_f, sigma=2.0, min_len=8, drop=0.1)
+            ref_s, ref_i = evdr.top_k(whole.score(Qf, qmf), k)
+            for mode in ("nccl", "peer"):
+                ss = evdr.ShardedSearch((ulo, uhi), mode=mode)
+                fs, fi = ss.search(ushard, Qf, qmf, k)
+                ok = ok and torch.equal(fi, ref_i) and torch.equal(fs, ref_s)
+                if nq_f == 1:
+                    gs = evdr.GraphedSearch(ss, ushard, nq_f, k)
+                    for _ in range(3):
+                        g_s, g_i = gs(Qf.float(), qmf)
+                        ok = ok and torch.equal(g_i, ref_i) and torch.equal(g_s, ref_s)
         # training collective: full (nq, n_pages) rows from the per-rank column blocks (unequal widths),
         # gradient of the local block = the local column slice
         loc = local.clone().requires_grad_(True)
