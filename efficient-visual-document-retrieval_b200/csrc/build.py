@@ -22,7 +22,7 @@ CSRC = Path(__file__).resolve().parent
 PKG = CSRC.parent
 OUT = PKG / "libevdr.so"
 BUILD = CSRC / "build"
-SOURCES = ["evdr_core.cu", "maxsim_simt.cu", "pack.cu", "topk.cu", "sharded.cu", "losses.cu", "train.cu", "maxsim_tc.cu"]
+SOURCES = ["evdr_core.cu", "maxsim_simt.cu", "pack.cu", "topk.cu", "sharded.cu", "losses.cu", "train.cu", "maxsim_tc.cu", "maxsim_scan.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "topk_dev.cuh", "../../include/evdr.h"]
 
 NVCC_FLAGS = [

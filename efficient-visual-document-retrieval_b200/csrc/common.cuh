@@ -92,6 +92,11 @@ namespace evdr {
 int scan_topk(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq, const void* tokens, int64_t n_tokens,
               const int32_t* chunk_off, int np, int64_t total_chunks, int k, int64_t id_offset, float* cand_s,
               long long* cand_i, int* n_cta, cudaStream_t st);
+// maxsim_scan.cu: the operand-swapped streaming scan for 1-2 queries (scores and / or per-CTA top-k lists)
+int scan_swapped(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq, const void* tokens, int64_t n_tokens,
+                 const int32_t* chunk_off, int np, int64_t total_chunks, int pages_per_item, float* out,
+                 int64_t out_ld, int tk_k, int64_t id_offset, float* cand_s, long long* cand_i, int* n_cta,
+                 cudaStream_t st);
 // topk.cu: k <= 32 best of (nq, ncand) candidate rows, one CTA per query, one launch
 int select_candidates(evdr_handle* h, const float* cand_s, const long long* cand_i, int nq, int ncand, int k,
                       float* top_s, long long* top_i, cudaStream_t st);

@@ -117,7 +117,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert((BN / 32) % 2 == 0, "the drain loop handles 32-column groups in pairs");
-  static_assert(EW == 4 || (EW == 8 && R == 2 && !CG2), "8 epilogue warps need R == 2, single-CTA");
+  static_assert(EW == 4 || (EW == 8 && R == 2), "8 epilogue warps need R == 2");
   static_assert(!TK || (!CG2 && !AM && !SP && KB == 1), "fused top-k: single-CTA bf16 scoring flavours, long-page epilogue");
   constexpr uint32_t IDESC = make_idesc_bf16(CG2 ? 256 : 128, BN);
   constexpr int CH_PER_TILE = BN / EVDR_CHUNK;
@@ -740,12 +740,23 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   prm.nqt = (nq + 3) / 4;
   // kernel flavour (EVDR_TC_MODE=pair selects the cta_group::2 kernels, for A/B runs)
   const char* mode = getenv("EVDR_TC_MODE");
-  const bool want_pair = mode && strcmp(mode, "pair") == 0;
+  if (mode && !*mode) mode = nullptr;
+  // one or two queries: the operand-swapped streaming scan (maxsim_scan.cu: page tokens on the M side, 4x / 2x
+  // fewer tensor cycles per byte -- the scan is power-bound as well as HBM-bound).  EVDR_TC_MODE=scan forces
+  // it, any other mode keeps the query-major kernels below.
+  if (nq <= 2 && !argmax && k_blocks == 1 && (!mode || strcmp(mode, "scan") == 0)) {
+    if (tk && tk->k > 32) return EVDR_ERR_UNSUPPORTED;
+    return scan_swapped(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, pages_per_item, out,
+                        out_ld, tk ? tk->k : 0, tk ? tk->id_offset : 0, tk ? tk->cand_s : nullptr,
+                        tk ? tk->cand_i : nullptr, tk ? &tk->n_cta : nullptr, static_cast<cudaStream_t>(stream));
+  }
+  const bool pair8 = mode && strcmp(mode, "pair8") == 0;      // CTA pairs with two epilogue groups (R = 2 per CTA)
+  const bool want_pair = mode && (strcmp(mode, "pair") == 0 || pair8);
   // single-CTA tiles are the default: measured 1443 vs 1282 TFLOP/s for CTA pairs at 1024 queries
   // (profiles/): both are power-capped, the pair hand-offs cross the cluster and cost utilisation
   const bool pair = want_pair && prm.nqt >= 2 && argmax == nullptr && k_blocks == 1;
   int R, tpg;
-  if (pair) { R = (prm.nqt + 1) / 2; if (R > 4) R = 4; tpg = 2 * R; }
+  if (pair) { R = (prm.nqt + 1) / 2; if (R > 4) R = 4; if (pair8) R = 2; tpg = 2 * R; }
   else { R = prm.nqt >= 3 ? 3 : prm.nqt; tpg = R; }
   if (argmax) { R = 3; tpg = 3; }   // the argmax variant is instantiated for R = 3 only
   if (k_blocks == 3) { R = 1; tpg = 1; }   // bf16x3: one resident query tile (96 KB), 64-token page tiles
@@ -838,6 +849,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   }
   if (argmax) return launch_tc<3, 256, 2, false, true>(h, Qb, tokens, n_tokens, prm, st);
   if (pair) {
+    if (pair8) return launch_tc<2, 256, 4, true, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 1) return launch_tc<1, 256, 6, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 2) return launch_tc<2, 256, 5, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 3) return launch_tc<3, 256, 4, true>(h, Qb, tokens, n_tokens, prm, st);
