@@ -35,6 +35,9 @@ namespace evdr {
 using namespace ptx;
 
 constexpr int A_HALF_BYTES = 128 * 64 * 2;       // one 64-wide K sub-tile (128 rows of 128 B)
+#ifndef EVDR_PAIR_MIN_TILES
+#define EVDR_PAIR_MIN_TILES 4                    // CTA pairs from this many query tiles (13 queries) on
+#endif
 
 struct TcParams {
   const uint8_t* qmask32;     // [nq, 32]
@@ -158,7 +161,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     // tmem_empty lives in the leader: 4 epilogue warps of each CTA of the pair arrive on it
     for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full(b), 1); mbar_init(bar_t_empty(b), CG2 ? 8 : 4); }
     // scheduler ring: the producer publishes item indices, the MMA thread + 4 epilogue warps consume
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), 1 + EW); }
+    // (pair mode: the leader draws for both CTAs; its slot_empty barriers also collect the peer's producer and
+    //  epilogue warps, the peer's slot_full barriers are armed by the leader's remote arrive)
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), (CG2 ? 2 : 1) * (1 + EW)); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -185,25 +190,33 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       const uint64_t pol = prm.stream_hint ? policy_evict_first() : policy_evict_last();
       int stage = 0, phase = 0, a_loads = 0, cur_g = -1;
       const uint32_t a_full_tx = CG2 ? mapa_u32(bar_a_full, 0) : bar_a_full;
-      // dynamic tile scheduler (single-CTA flavour): the producer draws the next item from a global
-      // counter and publishes it to the other roles through a small shared-memory ring, so all CTAs
-      // work on neighbouring items at any time and re-reads of a page block hit L2 however long the
-      // run is.  The pair flavour keeps the static round-robin deal.
+      // dynamic tile scheduler: the producer draws the next item from a global counter and publishes it to
+      // the other roles through a small shared-memory ring, so all CTAs work on neighbouring items at any
+      // time and re-reads of a page block hit L2 however long the run is.  In pair mode the leader CTA
+      // draws and also writes the item into the peer's ring through distributed shared memory.
       int sslot = 0, sphase = 0;
-      auto next_item = [&](int cur) -> int {
-        if constexpr (CG2) {
-          return cur < 0 ? unit : cur + n_units;
-        } else {
+      const uint32_t ring_u32 = sched_base + 8u * 2 * NSLOT;       // shared-memory address of item_ring[0]
+      auto next_item = [&](int) -> int {
+        int v;
+        if (!CG2 || rank == 0) {
           mbar_wait(bar_s_empty(sslot), sphase ^ 1);
-          const int v = atomicAdd(prm.sched, 1);
-          // every CTA draws exactly one terminal value (>= n_items); the CTA drawing the last of them
+          v = atomicAdd(prm.sched, 1);
+          // every drawing CTA draws exactly one terminal value (>= n_items); the one drawing the last of them
           // hands the counter back zeroed, so the next launch on this slot needs no memset
           if (v == n_items + n_units - 1) atomicExch(prm.sched, 0);
           item_ring[sslot] = v;
           mbar_arrive(bar_s_full(sslot));
-          if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
-          return v;
+          if constexpr (CG2) {   // the same item for the peer CTA: remote store, then a releasing remote arrive
+            st_shared_cluster_u32(mapa_u32(ring_u32 + 4u * sslot, 1), (uint32_t)v);
+            mbar_arrive_remote(mapa_u32(bar_s_full(sslot), 1));
+          }
+        } else {                 // peer CTA of a pair: consume what the leader published
+          mbar_wait_cluster(bar_s_full(sslot), sphase);
+          v = item_ring[sslot];
+          mbar_arrive_remote(mapa_u32(bar_s_empty(sslot), 0));
         }
+        if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
+        return v;
       };
       for (int it = next_item(-1); it < n_items; it = next_item(it)) {
         const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
@@ -255,16 +268,12 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       };
       int sslot = 0, sphase = 0;
       uint32_t use0 = 0, use1 = 0;
-      auto next_item = [&](int cur) -> int {
-        if constexpr (CG2) {
-          return cur < 0 ? unit : cur + n_units;
-        } else {
-          mbar_wait(bar_s_full(sslot), sphase);
-          const int v = item_ring[sslot];
-          mbar_arrive(bar_s_empty(sslot));
-          if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
-          return v;
-        }
+      auto next_item = [&](int) -> int {               // leader CTA only: its ring is filled locally
+        mbar_wait(bar_s_full(sslot), sphase);
+        const int v = item_ring[sslot];
+        mbar_arrive(bar_s_empty(sslot));
+        if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
+        return v;
       };
       for (int it = next_item(-1); it < n_items; it = next_item(it)) {
         const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
@@ -332,22 +341,23 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
       __syncwarp();
       if (lane == 0) {
         const uint32_t a = buf ? t_empty1 : t_empty0;
-        if constexpr (CG2) mbar_arrive_remote(a); else mbar_arrive(a);
+        if constexpr (CG2) mbar_arrive_remote_relaxed(a); else mbar_arrive(a);
       }
     };
 
     int sslot = 0, sphase = 0;
-    auto next_item = [&](int cur) -> int {
-      if constexpr (CG2) {
-        return cur < 0 ? unit : cur + n_units;
-      } else {
-        mbar_wait(bar_s_full(sslot), sphase);
-        const int v = item_ring[sslot];
-        __syncwarp();                                  // every lane has read the slot
-        if (lane == 0) mbar_arrive(bar_s_empty(sslot));
-        if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
-        return v;
+    const uint32_t s_empty_leader = CG2 ? mapa_u32(bar_s_empty(0), 0) : bar_s_empty(0);
+    auto next_item = [&](int) -> int {
+      if (CG2 && rank != 0) mbar_wait_cluster(bar_s_full(sslot), sphase);   // written by the leader CTA
+      else mbar_wait(bar_s_full(sslot), sphase);
+      const int v = item_ring[sslot];
+      __syncwarp();                                  // every lane has read the slot
+      if (lane == 0) {
+        if (CG2 && rank != 0) mbar_arrive_remote(s_empty_leader + 8u * sslot);
+        else mbar_arrive(bar_s_empty(sslot));
       }
+      if (++sslot == NSLOT) { sslot = 0; sphase ^= 1; }
+      return v;
     };
     for (int it = next_item(-1); it < n_items; it = next_item(it)) {
       const int g = it % prm.n_qgroups, pb = it / prm.n_qgroups;
@@ -688,7 +698,7 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
   prm.sched = nullptr;
-  if (!CG2) {
+  {
     // this launch's item counter: next slot of the handle's ring.  Slots start zeroed (evdr_create) and the
     // kernel hands its slot back zeroed (the CTA that draws the last terminal value resets it)
     prm.sched = h->sched_ring + (h->sched_next.fetch_add(1, std::memory_order_relaxed) % EVDR_SCHED_RING);
@@ -750,14 +760,27 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
                         out_ld, tk ? tk->k : 0, tk ? tk->id_offset : 0, tk ? tk->cand_s : nullptr,
                         tk ? tk->cand_i : nullptr, tk ? &tk->n_cta : nullptr, static_cast<cudaStream_t>(stream));
   }
-  const bool pair8 = mode && strcmp(mode, "pair8") == 0;      // CTA pairs with two epilogue groups (R = 2 per CTA)
-  const bool want_pair = mode && (strcmp(mode, "pair") == 0 || pair8);
-  // single-CTA tiles are the default: measured 1443 vs 1282 TFLOP/s for CTA pairs at 1024 queries
-  // (profiles/): both are power-capped, the pair hand-offs cross the cluster and cost utilisation
+  // CTA pairs (cta_group::2, M = 256: each CTA holds its own 128 query-token rows and HALF of the page tile,
+  // so per SM the shared-memory operand reads drop from 96 to 64 B/clk and the L2 -> SM page traffic halves)
+  // with two epilogue groups per CTA and the dynamic scheduler are the default from 4 query tiles on long
+  // pages: 1587 vs 1508 TFLOP/s at 1024 queries x 100k pages, 1405 vs 1316 at 32, 1311 vs 1191 at 16
+  // (profiles/r2_pair_vs_single_cta.log).  "pair" = the one-epilogue-group pair flavours (R = 1..4 per CTA),
+  // "1cta" / "ew8" / "sp8" / "ta" = the single-CTA flavours.
+  const double avg_chunks_all = (double)total_chunks / (double)np;
+  // A pair holds 4 query tiles per group; a group of 3 leaves one of the four 128-row slots idle.  The pair
+  // flavour is worth ~5 % (profiles/r2_pair_sweep.log: 100 queries = 25 tiles = 3 idle slots of 28 lose),
+  // so it is taken when at most 4 % of the slots would idle.
+  const int pair_groups = (prm.nqt + 3) / 4;
+  const int idle_slots = 4 * pair_groups - prm.nqt;
+  const bool pair8 = (mode && strcmp(mode, "pair8") == 0) ||
+                     (!mode && prm.nqt >= EVDR_PAIR_MIN_TILES && avg_chunks_all >= 32.0 &&
+                      25 * idle_slots <= 4 * pair_groups);
+  const bool want_pair = (mode && strcmp(mode, "pair") == 0) || pair8;
   const bool pair = want_pair && prm.nqt >= 2 && argmax == nullptr && k_blocks == 1;
   int R, tpg;
   if (pair) { R = (prm.nqt + 1) / 2; if (R > 4) R = 4; if (pair8) R = 2; tpg = 2 * R; }
   else { R = prm.nqt >= 3 ? 3 : prm.nqt; tpg = R; }
+  const bool pair8_on = pair && pair8;
   if (argmax) { R = 3; tpg = 3; }   // the argmax variant is instantiated for R = 3 only
   if (k_blocks == 3) { R = 1; tpg = 1; }   // bf16x3: one resident query tile (96 KB), 64-token page tiles
   // pages shorter than half a tile end several times per tile: the epilogue (not the MMA) is the
@@ -849,7 +872,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   }
   if (argmax) return launch_tc<3, 256, 2, false, true>(h, Qb, tokens, n_tokens, prm, st);
   if (pair) {
-    if (pair8) return launch_tc<2, 256, 4, true, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
+    if (pair8_on) return launch_tc<2, 256, 4, true, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 1) return launch_tc<1, 256, 6, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 2) return launch_tc<2, 256, 5, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 3) return launch_tc<3, 256, 4, true>(h, Qb, tokens, n_tokens, prm, st);

@@ -39,7 +39,7 @@ def test_medium_case(evdr, cuda):
     U.assert_scores_close(out.cpu().numpy(), z["out"])
 
 
-@pytest.mark.parametrize("mode", ["pair", "1cta", "default", "sp8", "ew8"])
+@pytest.mark.parametrize("mode", ["pair", "pair8", "1cta", "default", "sp8", "ew8"])
 @pytest.mark.parametrize("nq", [1, 3, 4, 5, 8, 9, 12, 13, 16, 17, 24, 25, 32, 33, 40, 100])
 def test_query_tile_configs_vs_exact_kernel(evdr, cuda, nq, mode, monkeypatch):
     """Every kernel flavour: one epilogue group with R = 1, 2, 3 resident query tiles ("1cta"), two
