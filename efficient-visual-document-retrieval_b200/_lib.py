@@ -20,6 +20,12 @@ TC_LQ = 32
 TC_LQ_MAX = 128      # longer queries are scored as up to 4 groups of 32 tokens
 TOPK_MAX = 128
 
+
+def row_blocks(k_blocks: int) -> int:
+    """128-wide K blocks STORED per operand row: 1 for plain bf16 (k_blocks = 1), 2 = [hi | lo] for the bf16x3
+    split (k_blocks = 3: the kernel forms the three products hi.hi + hi.lo + lo.hi from the two blocks)."""
+    return 2 if k_blocks == 3 else 1
+
 _lib = None
 _lock = threading.RLock()
 _handles: dict[int, C.c_void_p] = {}

@@ -59,14 +59,14 @@ def group_sum(scores: torch.Tensor, groups: int) -> torch.Tensor:
 
 
 def pack_queries(Q: torch.Tensor, qmask: torch.Tensor, k_blocks: int = 1):
-    """(nq, lq<=32, 128) -> bf16 (nq, 32, 128*k_blocks) with masked slots zeroed, uint8 (nq, 32).
-    k_blocks=3 writes the [hi | hi | lo] rows of the bf16x3 split."""
+    """(nq, lq<=32, 128) -> bf16 (nq, 32, 128) with masked slots zeroed, uint8 (nq, 32).
+    k_blocks=3 writes the [hi | lo] rows (256 wide) of the bf16x3 split."""
     _lib.require_cuda(Q, "Q")
     nq, lq, d = Q.shape
     Qc = _float_operand(Q)
     qm = _mask_u8(qmask)
     dev = Q.device
-    Qb = torch.empty((nq, TC_LQ, TC_DIM * k_blocks), dtype=torch.bfloat16, device=dev)
+    Qb = torch.empty((nq, TC_LQ, TC_DIM * _lib.row_blocks(k_blocks)), dtype=torch.bfloat16, device=dev)
     qm32 = torch.empty((nq, TC_LQ), dtype=torch.uint8, device=dev)
     lib = _lib.load()
     _lib.check(lib.evdr_pack_queries(_lib.handle(dev), Qc.data_ptr(), _lib.dtype_code(Qc), qm.data_ptr(),
@@ -80,8 +80,8 @@ class PackedPages:
 
     def __init__(self, tokens: torch.Tensor, chunk_off: torch.Tensor, n_pages: int, total_chunks: int,
                  page_offset: int = 0, k_blocks: int = 1):
-        self.k_blocks = int(k_blocks)   # 1 = bf16 rows, 3 = bf16x3 split rows [hi | lo | hi]
-        self.tokens = tokens            # bf16 [n_tokens, 128 * k_blocks]
+        self.k_blocks = int(k_blocks)   # 1 = bf16 rows, 3 = bf16x3 split: rows [hi | lo]
+        self.tokens = tokens            # bf16 [n_tokens, 128] or, for the split, [n_tokens, 256]
         self.chunk_off = chunk_off      # int32 [n_pages + 1]
         self.n_pages = int(n_pages)
         self.total_chunks = int(total_chunks)
@@ -98,7 +98,7 @@ class PackedPages:
         student tensor).  varlen=True trims each page after its last valid token (one device->host
         read of the total; right for a corpus that is packed once).
         normalize=True fuses l2_normalize(P * pmask[..., None]) (mainv2_iter_listwise.py:280).
-        k_blocks=3 stores the bf16x3 split (3x the bytes, near-fp32 similarities).
+        k_blocks=3 stores the bf16x3 split (2x the bytes, 3x the tensor work, near-fp32 similarities).
         """
         _lib.require_cuda(P, "P")
         npg, lp, d = P.shape
@@ -117,7 +117,7 @@ class PackedPages:
             total = int(chunk_off[-1].item())
         else:
             total = npg * ((lp + CHUNK - 1) // CHUNK)
-        tokens = torch.empty((total * CHUNK, TC_DIM * k_blocks), dtype=torch.bfloat16, device=dev)
+        tokens = torch.empty((total * CHUNK, TC_DIM * _lib.row_blocks(k_blocks)), dtype=torch.bfloat16, device=dev)
         _lib.check(lib.evdr_pack_pages(h, Pc.data_ptr(), _lib.dtype_code(Pc), pm.data_ptr(),
                                        chunk_off.data_ptr(), npg, lp, d, 1 if normalize else 0, k_blocks,
                                        tokens.data_ptr(), st), "evdr_pack_pages")
@@ -168,7 +168,7 @@ class PackedPages:
         _lib.check(lib.evdr_pack_plan_ragged(h, mask_d.data_ptr(), off_d.data_ptr(), npg, chunk_off.data_ptr(), st),
                    "evdr_pack_plan_ragged")
         total = int(chunk_off[-1].item())
-        tokens = torch.empty((total * CHUNK, TC_DIM * k_blocks), dtype=torch.bfloat16, device=device)
+        tokens = torch.empty((total * CHUNK, TC_DIM * _lib.row_blocks(k_blocks)), dtype=torch.bfloat16, device=device)
         _lib.check(lib.evdr_pack_pages_ragged(h, tok_d.data_ptr(), _lib.EVDR_F32, mask_d.data_ptr(), off_d.data_ptr(),
                                               chunk_off.data_ptr(), npg, max(1, int(lens.max()) if npg else 1),
                                               TC_DIM, 1 if normalize else 0, k_blocks, tokens.data_ptr(), st),
@@ -216,7 +216,7 @@ class PackedPages:
                    "evdr_pack_plan_ragged")
         # every page has at least one chunk and ceil(len/16) otherwise: known on the host, no device read
         total = sum(max(1, (int(l) + CHUNK - 1) // CHUNK) for l in lens_t.tolist())
-        tokens = torch.empty((total * CHUNK, TC_DIM * k_blocks), dtype=torch.bfloat16, device=device)
+        tokens = torch.empty((total * CHUNK, TC_DIM * _lib.row_blocks(k_blocks)), dtype=torch.bfloat16, device=device)
         _lib.check(lib.evdr_pack_pages_ragged(h, flat.data_ptr(), _lib.EVDR_F32, mask_d.data_ptr(), off_d.data_ptr(),
                                               chunk_off.data_ptr(), npg, max(1, max_len), TC_DIM,
                                               1 if normalize else 0, k_blocks, tokens.data_ptr(), st),

@@ -62,9 +62,10 @@ struct TcParams {
   long long id_offset;
 };
 
-// KB = number of 128-wide K blocks of the operands: 1 = plain bf16; 3 = the bf16x3 split
-// A = [Qhi | Qhi | Qlo], B = [Phi | Plo | Phi] whose K = 384 contraction is Qhi.Phi + Qhi.Plo + Qlo.Phi,
-// i.e. the fp32 dot product up to the dropped Qlo.Plo term (~2^-18 relative) -- the high-fidelity mode
+// KB: 1 = plain bf16 operands (K = 128); 3 = the bf16x3 split: both operands are stored as TWO 128-wide
+// K blocks [hi | lo] (hi = bf16(x), lo = bf16(x - hi)) and the MMA issuer runs THREE K = 128 products
+// into the same accumulator, Qhi.Phi + Qhi.Plo + Qlo.Phi, by pointing the descriptors at the matching
+// blocks -- the fp32 dot product up to the dropped Qlo.Plo term (~2^-18 relative), the high-fidelity mode
 // TA: the resident query tiles (A operand) live in TENSOR MEMORY instead of shared memory: the epilogue
 // warps copy their query's 32 token rows global -> registers -> TMEM (tcgen05.st) at every item change and
 // the MMAs take A from TMEM.  Shared-memory operand reads drop from 96 to 64 B/clk per SM (only the page
@@ -73,7 +74,8 @@ struct TcParams {
 template <int R, int BN, int STAGES, bool CG2, int KB = 1, bool SP = false, int EW = 4, bool TA = false>
 struct TcCfg {
   static constexpr int B_ROWS = CG2 ? BN / 2 : BN;          // page tokens held by this CTA per stage
-  static constexpr int KSUB = 2 * KB;                        // 64-wide K sub-tiles per operand tile
+  static constexpr int KSUB = (KB == 3) ? 4 : 2 * KB;        // 64-wide K sub-tiles STORED per operand tile
+  static constexpr int KSTEPS = (KB == 3) ? 24 : 8 * KB;      // K = 16 MMA steps per pass
   static constexpr int B_HALF_BYTES = B_ROWS * 64 * 2;       // one 64-wide K sub-tile
   static constexpr int B_STAGE_BYTES = KSUB * B_HALF_BYTES;
   static constexpr int A_TILE_BYTES = KSUB * A_HALF_BYTES;
@@ -300,9 +302,12 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             const uint32_t d_tmem = tmem_base + buf * BN;
             const uint32_t a_base = sA + r * A_TILE_BYTES;
 #pragma unroll
-            for (int k = 0; k < 4 * KSUB; ++k) {
-              const uint64_t da = make_sw128_desc(a_base + (k >> 2) * A_HALF_BYTES + (k & 3) * 32);
-              const uint64_t db = make_sw128_desc(b_base + (k >> 2) * S::B_HALF_BYTES + (k & 3) * 32);
+            for (int k = 0; k < S::KSTEPS; ++k) {
+              // bf16x3: steps 0-7 hi.hi, 8-15 Qhi.Plo, 16-23 Qlo.Phi (largest product first)
+              const int ka = (KB == 3) ? ((k >> 3) == 2 ? 2 : 0) + ((k & 7) >> 2) : (k >> 2);
+              const int kb = (KB == 3) ? ((k >> 3) == 1 ? 2 : 0) + ((k & 7) >> 2) : (k >> 2);
+              const uint64_t da = make_sw128_desc(a_base + ka * A_HALF_BYTES + (k & 3) * 32);
+              const uint64_t db = make_sw128_desc(b_base + kb * S::B_HALF_BYTES + (k & 3) * 32);
               if constexpr (CG2) mma_bf16_ss_cg2(d_tmem, da, db, IDESC, k > 0);
               else if constexpr (TA) mma_bf16_ts(d_tmem, tmem_base + S::A_COL + r * 64 + k * 8, db, IDESC, k > 0);
               else mma_bf16_ss(d_tmem, da, db, IDESC, k > 0);
@@ -670,9 +675,10 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
   using S = TcCfg<R, BN, STAGES, CG2, KB, SP, EW, TA>;
   prm.qb = static_cast<const __nv_bfloat16*>(Qb);
   CUtensorMap tmQ, tmP;
-  int rc = encode_2d_bf16(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, 128, KB, "queries");
+  constexpr int STORED = (KB == 3) ? 2 : KB;                  // 128-wide K blocks per stored row
+  int rc = encode_2d_bf16(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, 128, STORED, "queries");
   if (rc != EVDR_OK) return rc;
-  rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, KB, "page tokens");
+  rc = encode_2d_bf16(h, &tmP, tokens, (uint64_t)n_tokens, S::B_ROWS, STORED, "page tokens");
   if (rc != EVDR_OK) return rc;
   auto kern = maxsim_tc_kernel<R, BN, STAGES, CG2, AM, KB, SP, EW, TA, TK>;
   if ((size_t)S::TOTAL > h->smem_optin)
@@ -776,13 +782,18 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
                      (!mode && prm.nqt >= EVDR_PAIR_MIN_TILES && avg_chunks_all >= 32.0 &&
                       25 * idle_slots <= 4 * pair_groups);
   const bool want_pair = (mode && strcmp(mode, "pair") == 0) || pair8;
-  const bool pair = want_pair && prm.nqt >= 2 && argmax == nullptr && k_blocks == 1;
+  // bf16x3: one resident query tile per CTA (64 KB) and 2 x 64 KB page-tile stages; CTA pairs (2 query tiles
+  // per page tile, half a tile per CTA: 21 instead of 42 B/clk of L2 -> SM traffic per SM) unless an odd tile
+  // count would idle more than ~10 % of the slots
+  const bool pair_x3 = k_blocks == 3 && !argmax && prm.nqt >= 2 && (prm.nqt % 2 == 0 || prm.nqt >= 9) &&
+                       (!mode || strcmp(mode, "1cta") != 0);
+  const bool pair = (want_pair && prm.nqt >= 2 && argmax == nullptr && k_blocks == 1) || pair_x3;
   int R, tpg;
   if (pair) { R = (prm.nqt + 1) / 2; if (R > 4) R = 4; if (pair8) R = 2; tpg = 2 * R; }
   else { R = prm.nqt >= 3 ? 3 : prm.nqt; tpg = R; }
   const bool pair8_on = pair && pair8;
   if (argmax) { R = 3; tpg = 3; }   // the argmax variant is instantiated for R = 3 only
-  if (k_blocks == 3) { R = 1; tpg = 1; }   // bf16x3: one resident query tile (96 KB), 64-token page tiles
+  if (k_blocks == 3) { R = 1; tpg = pair_x3 ? 2 : 1; }
   // pages shorter than half a tile end several times per tile: the epilogue (not the MMA) is the
   // limit there -> two epilogue groups, one per resident query tile
   // Two epilogue groups (8 warps, R = 2) measured best whenever there are enough query tiles to
@@ -816,7 +827,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     // ... with few query groups every page block is re-read by only a handful of CTAs while the grid
     // spans units / n_qgroups blocks: keep that window L2-resident (~48 MB of the 126 MB) ...
     if (n_qgroups > 1 && n_qgroups < 8) {
-      const double cap = 48e6 * n_qgroups / ((double)units * avg_tok * EVDR_TC_DIM * 2 * k_blocks);
+      const double cap = 48e6 * n_qgroups / ((double)units * avg_tok * EVDR_TC_DIM * 2 * (k_blocks == 3 ? 2 : 1));
       if (ppi > cap) ppi = cap < 8.0 ? 8 : (int)cap;   // >= 8 pages: keep the query-tile reload amortised
     } else if (n_qgroups >= 8 && n_qgroups < 64) {
       // ... from 8 groups on the CTAs of a block run in step (dynamic scheduler) and the window is not
@@ -833,7 +844,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     // P passes per CTA in total, items of p passes lose ~3.5/p to reloads and ~p/(2P) to the tail: the optimum
     // is p = sqrt(7 P).  Items stay within the caps above and never fewer than one per CTA.
     {
-      const int bn = (k_blocks == 3) ? 64 : (want_ta ? 192 : 256);
+      const int bn = (k_blocks == 3) ? (pair_x3 ? 256 : 128) : (want_ta ? 192 : 256);
       const double avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
       const double passes_per_cta = (double)total_chunks * EVDR_CHUNK / bn * prm.nqt / (double)units;
       const double item_passes = sqrt(7.0 * passes_per_cta);
@@ -867,8 +878,9 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     return launch_tc<1, 256, 3, false, false, 1, false, 4, false, true>(h, Qb, tokens, n_tokens, prm, st);
   }
   if (k_blocks == 3) {
-    if (argmax) return launch_tc<1, 64, 2, false, true, 3>(h, Qb, tokens, n_tokens, prm, st);
-    return launch_tc<1, 64, 2, false, false, 3>(h, Qb, tokens, n_tokens, prm, st);
+    if (argmax) return launch_tc<1, 128, 2, false, true, 3>(h, Qb, tokens, n_tokens, prm, st);
+    if (pair_x3) return launch_tc<1, 256, 2, true, false, 3>(h, Qb, tokens, n_tokens, prm, st);
+    return launch_tc<1, 128, 2, false, false, 3>(h, Qb, tokens, n_tokens, prm, st);
   }
   if (argmax) return launch_tc<3, 256, 2, false, true>(h, Qb, tokens, n_tokens, prm, st);
   if (pair) {

@@ -143,7 +143,7 @@ pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
   }
   __syncthreads();
 
-  const int row = EVDR_TC_DIM * kb;        // kb = 3: [hi | lo | hi] rows of the bf16x3 split
+  const int row = EVDR_TC_DIM * (kb == 3 ? 2 : 1);   // kb = 3 (bf16x3 split): [hi | lo] rows of 256
   __nv_bfloat16* dst = tokens + (size_t)c0 * CH * row;
   const T* Pc = P + base * EVDR_TC_DIM;
   for (int m = warp; m < n_slots; m += (blockDim.x >> 5)) {
@@ -163,7 +163,6 @@ pack_pages_kernel(const T* __restrict__ P, const uint8_t* __restrict__ pmask,
     if (kb == 3) {
       const uint2 lo = pack_bf16x4(residual_bf16x4(v, hi));
       *reinterpret_cast<uint2*>(dst + (size_t)m * row + EVDR_TC_DIM + lane * 4) = lo;
-      *reinterpret_cast<uint2*>(dst + (size_t)m * row + 2 * EVDR_TC_DIM + lane * 4) = hi;
     }
   }
 }
@@ -179,13 +178,12 @@ pack_queries_kernel(const T* __restrict__ Q, const uint8_t* __restrict__ qmask, 
   const bool valid = (n < lq) && qmask[(size_t)q * lq + n] != 0;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (valid) v = load4(Q + ((size_t)q * lq + n) * EVDR_TC_DIM + lane * 4);
-  const int row = EVDR_TC_DIM * kb;        // kb = 3: [hi | hi | lo] rows of the bf16x3 split
+  const int row = EVDR_TC_DIM * (kb == 3 ? 2 : 1);   // kb = 3 (bf16x3 split): [hi | lo] rows of 256
   const uint2 hi = pack_bf16x4(v);
   *reinterpret_cast<uint2*>(Qb + (size_t)slot * row + lane * 4) = hi;
   if (kb == 3) {
     const uint2 lo = pack_bf16x4(residual_bf16x4(v, hi));
-    *reinterpret_cast<uint2*>(Qb + (size_t)slot * row + EVDR_TC_DIM + lane * 4) = hi;
-    *reinterpret_cast<uint2*>(Qb + (size_t)slot * row + 2 * EVDR_TC_DIM + lane * 4) = lo;
+    *reinterpret_cast<uint2*>(Qb + (size_t)slot * row + EVDR_TC_DIM + lane * 4) = lo;
   }
   if (lane == 0) qmask32[slot] = valid ? 1 : 0;
 }

@@ -37,10 +37,10 @@ extern "C" int evdr_maxsim_train_fwd(evdr_handle* h, const void* Q, int q_dtype,
                                       : (groups > 1 ? (size_t)nq_g * np * sizeof(float) : 0);
   if ((size_t)np * R * sizeof(int32_t) > ((size_t)1 << 30) || np > 65535)
     return set_error(EVDR_ERR_UNSUPPORTED, "evdr_maxsim_train_fwd: np*nq*lq too large for one call");
-  const size_t b_q = align256((size_t)nq_g * EVDR_TC_LQ * EVDR_TC_DIM * 3 * 2);
+  const size_t b_q = align256((size_t)nq_g * EVDR_TC_LQ * EVDR_TC_DIM * 2 * 2);   // [hi | lo] rows
   const size_t b_m = align256((size_t)nq_g * EVDR_TC_LQ);
   const size_t b_o = align256(((size_t)np + 1) * sizeof(int32_t));
-  const size_t b_t = align256(total_chunks * EVDR_CHUNK * EVDR_TC_DIM * 3 * 2);
+  const size_t b_t = align256(total_chunks * EVDR_CHUNK * EVDR_TC_DIM * 2 * 2);
   const size_t b_r = align256(rowmax_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned char* ws = nullptr;

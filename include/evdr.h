@@ -119,9 +119,9 @@ EVDR_API int evdr_maxsim_bwd(evdr_handle* h,
  *   as evaluator/retrieval.py:192,204).  normalize != 0 fuses the reference's
  *   `l2_normalize(P * pmask[...,None])` (utils/preprocess_data.py:8-9,
  *   mainv2_iter_listwise.py:280) in fp32 before the bf16 rounding.
- * k_blocks: 1 = plain bf16 rows of 128; 3 = the bf16x3 split for near-fp32 fidelity: page rows are
- *   [hi | lo | hi] and query rows [hi | hi | lo] of 384 bf16 (hi = bf16(x), lo = bf16(x - hi)), whose
- *   K = 384 contraction is Qhi.Phi + Qhi.Plo + Qlo.Phi = <Q,P> up to a 2^-18 relative term.
+ * k_blocks: 1 = plain bf16 rows of 128; 3 = the bf16x3 split for near-fp32 fidelity: page AND query rows are
+ *   [hi | lo] of 256 bf16 (hi = bf16(x), lo = bf16(x - hi)); the kernel runs the three K = 128 products
+ *   Qhi.Phi + Qhi.Plo + Qlo.Phi into one accumulator = <Q,P> up to a 2^-18 relative term.
  * ------------------------------------------------------------------------ */
 EVDR_API int evdr_pack_plan(evdr_handle* h, const uint8_t* pmask_dev, int np, int lp,
                             int varlen, int32_t* chunk_off_dev, void* stream);
@@ -150,8 +150,8 @@ EVDR_API int evdr_pack_queries(evdr_handle* h, const void* Q_dev, int q_dtype,
  * row-max over page tokens and the query-token sum are fused into the epilogue,
  * the similarity matrix never leaves the SM.  Persistent kernel, one CTA per SM.
  *
- *   tokens_dev : bf16 [n_tokens, 128*k_blocks], n_tokens >= 16*chunk_off[np] (the stream);
- *   Qb_dev     : bf16 [nq, 32, 128*k_blocks] from evdr_pack_queries;
+ *   tokens_dev : bf16 [n_tokens, 128] (k_blocks = 1) or [n_tokens, 256] (k_blocks = 3), n_tokens >= 16*chunk_off[np];
+ *   Qb_dev     : bf16 [nq, 32, 128 | 256] from evdr_pack_queries with the same k_blocks;
  *   out_dev    : fp32 [nq, out_ld], column c = page c.
  * The base addresses must be 16-byte aligned (TMA).  `pages_per_item` <= 0 lets
  * the library pick the work-item size.

@@ -113,7 +113,7 @@ def test_packed_stream_stays_inside_its_buffer(evdr, cuda, npg, lp, varlen, kb):
     assert bool((off[:8] == SENT_I).all() and (off[8 + npg + 1:] == SENT_I).all())
     total = int(off[8 + npg].item())
     assert total >= npg
-    width = 128 * kb
+    width = 128 * evdr._lib.row_blocks(kb)
     pad = 4 * width
     tok = torch.full((total * 16 * width + 2 * pad,), 7.0, dtype=torch.bfloat16, device=cuda)
     evdr._lib.check(lib.evdr_pack_pages(h, P.data_ptr(), 0, pm.data_ptr(), off[8:].data_ptr(), npg, lp, 128, 1, kb,
