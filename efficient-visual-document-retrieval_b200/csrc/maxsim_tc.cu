@@ -79,14 +79,17 @@ struct TcCfg {
   static constexpr int B_HALF_BYTES = B_ROWS * 64 * 2;       // one 64-wide K sub-tile
   static constexpr int B_STAGE_BYTES = KSUB * B_HALF_BYTES;
   static constexpr int A_TILE_BYTES = KSUB * A_HALF_BYTES;
-  static constexpr int A_BYTES = TA ? 0 : R * A_TILE_BYTES;
+  // NA = 2 (the CTA-pair flavour with two epilogue groups): the query tiles of the NEXT query group are loaded
+  // into a second buffer while the MMAs of the current item drain, so an item change costs no idle tensor time
+  static constexpr int NA = (CG2 && EW == 8 && KB == 1) ? 2 : 1;
+  static constexpr int A_BYTES = TA ? 0 : NA * R * A_TILE_BYTES;
   static constexpr int A_COL = 2 * BN;                       // TA: first TMEM column of query tile 0
   static constexpr int B_BYTES = STAGES * B_STAGE_BYTES;
   static constexpr int BAR_OFF = A_BYTES + B_BYTES;
   // barriers: full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2], tmem ptr,
   // then the scheduler ring: slot_full[NSLOT], slot_empty[NSLOT], item[NSLOT]
   static constexpr int NSLOT = 4;
-  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 6) + 8 + 8 * 2 * NSLOT + 4 * NSLOT;
+  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 6) + 8 + 8 * 2 * NSLOT + 4 * NSLOT + 16;   // + a_full / a_empty of buffer 1
   // short-page variant: per epilogue warp a [16 pages][32 tokens (+1 pad)] fp32 staging area where the
   // per-token maxes of the pages completed in a tile wait for their 32-token sums
   static constexpr int STG_ROW = 33;
@@ -134,8 +137,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   const uint32_t bars = smem_base + S::BAR_OFF;
   auto bar_full = [&](int s) { return bars + 8u * s; };
   auto bar_empty = [&](int s) { return bars + 8u * (STAGES + s); };
-  const uint32_t bar_a_full = bars + 8u * (2 * STAGES);
-  const uint32_t bar_a_empty = bars + 8u * (2 * STAGES + 1);
+  constexpr int NA = S::NA;
+  const uint32_t bar_a_extra = bars + 8u * (2 * STAGES + 6) + 8u + 8u * 2 * S::NSLOT + 4u * S::NSLOT;
+  auto bar_a_full = [&](int b) { return b == 0 ? bars + 8u * (2 * STAGES) : bar_a_extra; };
+  auto bar_a_empty = [&](int b) { return b == 0 ? bars + 8u * (2 * STAGES + 1) : bar_a_extra + 8u; };
   auto bar_t_full = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
   auto bar_t_empty = [&](int b) { return bars + 8u * (2 * STAGES + 4 + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 6);
@@ -158,8 +163,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapP);
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    mbar_init(bar_a_full, TA ? EW : 1);       // TA: every epilogue warp arrives after staging its rows
-    mbar_init(bar_a_empty, 1);
+    for (int b = 0; b < NA; ++b) {
+      mbar_init(bar_a_full(b), TA ? EW : 1);    // TA: every epilogue warp arrives after staging its rows
+      mbar_init(bar_a_empty(b), 1);
+    }
     // tmem_empty lives in the leader: 4 epilogue warps of each CTA of the pair arrive on it
     for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full(b), 1); mbar_init(bar_t_empty(b), CG2 ? 8 : 4); }
     // scheduler ring: the producer publishes item indices, the MMA thread + 4 epilogue warps consume
@@ -191,7 +198,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     if (lane == 0) {
       const uint64_t pol = prm.stream_hint ? policy_evict_first() : policy_evict_last();
       int stage = 0, phase = 0, a_loads = 0, cur_g = -1;
-      const uint32_t a_full_tx = CG2 ? mapa_u32(bar_a_full, 0) : bar_a_full;
+
       // dynamic tile scheduler: the producer draws the next item from a global counter and publishes it to
       // the other roles through a small shared-memory ring, so all CTAs work on neighbouring items at any
       // time and re-reads of a page block hit L2 however long the run is.  In pair mode the leader CTA
@@ -227,15 +234,18 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         const int ntile = ((c1 - c0) * EVDR_CHUNK + BN - 1) / BN;
         const int rc = passes_in_group(g);
         if (!TA && g != cur_g) {
-          if (a_loads > 0) mbar_wait(bar_a_empty, (a_loads - 1) & 1);
+          const int ab = a_loads % NA;
+          if (a_loads >= NA) mbar_wait(bar_a_empty(ab), ((a_loads / NA) - 1) & 1);
+          const uint32_t a_full_tx = CG2 ? mapa_u32(bar_a_full(ab), 0) : bar_a_full(ab);
+          const uint32_t a_dst = sA + ab * (R * A_TILE_BYTES);
           // out-of-range query tiles are zero-filled by TMA and still count their bytes
-          if (rank == 0) mbar_expect_tx(bar_a_full, (CG2 ? 2 : 1) * rc * A_TILE_BYTES);
+          if (rank == 0) mbar_expect_tx(bar_a_full(ab), (CG2 ? 2 : 1) * rc * A_TILE_BYTES);
           for (int r = 0; r < rc; ++r) {
             const int tile = group_start(g) + (CG2 ? 2 * r + rank : r);
 #pragma unroll
             for (int kk = 0; kk < KSUB; ++kk) {
-              if constexpr (CG2) tma_load_2d_cg2(sA + r * A_TILE_BYTES + kk * A_HALF_BYTES, &tmapQ, a_full_tx, kk * 64, tile * 128);
-              else tma_load_2d(sA + r * A_TILE_BYTES + kk * A_HALF_BYTES, &tmapQ, a_full_tx, kk * 64, tile * 128);
+              if constexpr (CG2) tma_load_2d_cg2(a_dst + r * A_TILE_BYTES + kk * A_HALF_BYTES, &tmapQ, a_full_tx, kk * 64, tile * 128);
+              else tma_load_2d(a_dst + r * A_TILE_BYTES + kk * A_HALF_BYTES, &tmapQ, a_full_tx, kk * 64, tile * 128);
             }
           }
           ++a_loads;
@@ -263,7 +273,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   } else if (warp == 1) {
     // ===================================================== MMA issuer (one thread, leader CTA)
     if (lane == 0 && rank == 0) {
-      int stage = 0, phase = 0, a_phase = 0, cur_g = -1;
+      int stage = 0, phase = 0, a_uses = 0, a_cur = 0, cur_g = -1;
       uint32_t acc_it = 0;
       auto commit = [&](uint32_t bar) {
         if constexpr (CG2) mma_commit_cg2_mc(bar, (uint16_t)0x3); else mma_commit(bar);
@@ -284,9 +294,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
         const int ntile = ((c1 - c0) * EVDR_CHUNK + BN - 1) / BN;
         const int rc = passes_in_group(g);
         if (g != cur_g) {
-          if (!TA && cur_g != -1) commit(bar_a_empty);  // previous A tiles free once their MMAs retire
-          mbar_wait(bar_a_full, a_phase);
-          a_phase ^= 1;
+          if (!TA && cur_g != -1) commit(bar_a_empty(a_cur));  // previous A tiles free once their MMAs retire
+          a_cur = a_uses % NA;
+          mbar_wait(bar_a_full(a_cur), (a_uses / NA) & 1);
+          ++a_uses;
           tc_fence_after();
           cur_g = g;
         }
@@ -300,7 +311,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
             mbar_wait(bar_t_empty(buf), (nuse & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * BN;
-            const uint32_t a_base = sA + r * A_TILE_BYTES;
+            const uint32_t a_base = sA + a_cur * (R * A_TILE_BYTES) + r * A_TILE_BYTES;
 #pragma unroll
             for (int k = 0; k < S::KSTEPS; ++k) {
               // bf16x3: steps 0-7 hi.hi, 8-15 Qhi.Plo, 16-23 Qlo.Phi (largest product first)
@@ -405,7 +416,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a_full);
+          if (lane == 0) mbar_arrive(bar_a_full(0));
         }
         cur_g = g;
       }
@@ -884,7 +895,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   }
   if (argmax) return launch_tc<3, 256, 2, false, true>(h, Qb, tokens, n_tokens, prm, st);
   if (pair) {
-    if (pair8_on) return launch_tc<2, 256, 4, true, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
+    if (pair8_on) return launch_tc<2, 256, 3, true, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 1) return launch_tc<1, 256, 6, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 2) return launch_tc<2, 256, 5, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 3) return launch_tc<3, 256, 4, true>(h, Qb, tokens, n_tokens, prm, st);
