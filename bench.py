@@ -7,17 +7,23 @@
 A "step" is one pass of the hot path over one batch: 1024 queries (32 tokens, 128-d) scored against
 this rank's 100 000-page shard (1030 valid tokens per page, stored as 1040 bf16 slots) with the
 tcgen05 MaxSim kernel, followed by the local top-10 and -- for N > 1 -- the exchange + merge of the
-candidates (one peer-memory kernel over NVLink by default, ncclAllGather + merge with --exchange
-nccl).  BASELINE.json configs[2] per GPU; the corpus grows with N: weak scaling.
+candidates (ncclAllGather + merge is the headline; the one-kernel peer-memory exchange over NVLink is timed
+beside it, --exchange selects).  BASELINE.json configs[2] per GPU; the corpus grows with N: weak scaling.
 
 value     : whole-job pairs/s with everything resident in HBM (CUDA events, max over ranks)
 e2e       : same metric through the reference-facing call score_multi_vector_masked(Q, P, qmask,
             pmask) with the query batch copied from pinned host memory and the (nq, np) score matrix
             read back to the host inside the timed region, every step
-roofline  : dominant kernel (maxsim_tc_kernel) alone: algorithmic FLOPs / CUDA-event duration vs the
-            measured bf16 peak of MEASURED_PEAKS.json
-cpu_baseline / --impl reference : the reference's algorithm (oracle port, torch CPU, all host
-            threads) on a bounded sample of the same workload
+roofline  : dominant kernel (maxsim_tc_kernel) timed with CUDA events INSIDE the timed steps: algorithmic
+            FLOPs / duration vs the measured bf16 peak of MEASURED_PEAKS.json
+cpu_baseline / --impl reference : the reference's OWN score_multi_vector_masked (unmodified file staged in
+            baseline/_ref by tools/stage_reference.py; kind "reference") on the box's host cores, all
+            threads, on a fixed bounded sample of the workload (config.reference_arm_sample)
+gpu_reference : the same unmodified function, torch eager on this B200 (N = 1)
+sharded_check (N > 1) : merged top-10 identical on every rank and equal to torch.topk of the all-gathered rows
+extras    : single-query streaming scan (HBM roofline), 16 / 32 / 64-query batches (each back to back AND
+            duty-cycled, with its own nvidia-smi clock / power record), corpus in pinned host memory,
+            top-10 QPS on a 1 M-page corpus sharded over the box (N >= 2; 500 k pages at N = 1)
 """
 from __future__ import annotations
 
@@ -410,7 +416,8 @@ def main():
     # denominator: the measured BURST cuBLAS bf16 peak (the higher of the two measured figures, so the
     # fraction can only be understated); each launch runs ~0.57 s at the power cap, where cuBLAS itself
     # sustains bf16_tflops_sustained -- reported beside it
-    roofline = {"kernel": "maxsim_tc_kernel", "bound": "tensor", "achieved": achieved,
+    roofline = {"kernel": "maxsim_tc_kernel<2,256,3,CG2,...,EW=8> (cta_group::2 pairs, two epilogue groups)",
+                "bound": "tensor", "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"],
                 "peak_kind": f"{peaks['source']} burst cuBLAS bf16 (8192^3, best of 10)",
@@ -679,7 +686,7 @@ def side_measurements(evdr, torch, pk, corpus, dev, peaks, timed, search, n_gpus
         gbs = pages_s * BYTES_PER_PAGE / 1e9
         tf = nq * npg * FLOPS_PER_PAIR / (ms_scan * 1e-3) / 1e12
         if nq == 1:
-            rec["roofline"] = {"kernel": "maxsim_tc_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+            rec["roofline"] = {"kernel": "maxsim_scan_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": measured_traffic(nq, npg),
                                "algorithmic_bytes_per_launch": npg * BYTES_PER_PAGE,
                                "achieved_duty_cycled": npg * BYTES_PER_PAGE / (ms_iso * 1e-3) / 1e9}
