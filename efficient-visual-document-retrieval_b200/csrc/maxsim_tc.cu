@@ -81,7 +81,7 @@ struct TcCfg {
   static constexpr int A_TILE_BYTES = KSUB * A_HALF_BYTES;
   // NA = 2 (the CTA-pair flavour with two epilogue groups): the query tiles of the NEXT query group are loaded
   // into a second buffer while the MMAs of the current item drain, so an item change costs no idle tensor time
-  static constexpr int NA = (CG2 && EW == 8 && KB == 1) ? 2 : 1;
+  static constexpr int NA = (CG2 && EW == 8 && KB == 1 && !SP) ? 2 : 1;   // (SP: the staging rows need the room)
   static constexpr int A_BYTES = TA ? 0 : NA * R * A_TILE_BYTES;
   static constexpr int A_COL = 2 * BN;                       // TA: first TMEM column of query tile 0
   static constexpr int B_BYTES = STAGES * B_STAGE_BYTES;
@@ -790,8 +790,10 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   const int pair_groups = (prm.nqt + 3) / 4;
   const int idle_slots = 4 * pair_groups - prm.nqt;
   const bool pair8 = (mode && strcmp(mode, "pair8") == 0) ||
-                     (!mode && prm.nqt >= EVDR_PAIR_MIN_TILES && avg_chunks_all >= 32.0 &&
-                      25 * idle_slots <= 4 * pair_groups);
+                     (!mode && prm.nqt >= EVDR_PAIR_MIN_TILES && 25 * idle_slots <= 4 * pair_groups);
+  // pages shorter than two tiles on average: the pair flavour with the short-page (end-mask + staged-sum)
+  // epilogue -- 1560 vs 1464 TFLOP/s on 64-token pages at 1024 queries (profiles/r2_short_pages_pair.log)
+  const bool pair_sp = pair8 && avg_chunks_all < 32.0;
   const bool want_pair = (mode && strcmp(mode, "pair") == 0) || pair8;
   // bf16x3: one resident query tile per CTA (64 KB) and 2 x 64 KB page-tile stages; CTA pairs (2 query tiles
   // per page tile, half a tile per CTA: 21 instead of 42 B/clk of L2 -> SM traffic per SM) unless an odd tile
@@ -895,6 +897,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   }
   if (argmax) return launch_tc<3, 256, 2, false, true>(h, Qb, tokens, n_tokens, prm, st);
   if (pair) {
+    if (pair8_on && pair_sp) return launch_tc<2, 256, 4, true, false, 1, true, 8>(h, Qb, tokens, n_tokens, prm, st);
     if (pair8_on) return launch_tc<2, 256, 3, true, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 1) return launch_tc<1, 256, 6, true>(h, Qb, tokens, n_tokens, prm, st);
     if (R == 2) return launch_tc<2, 256, 5, true>(h, Qb, tokens, n_tokens, prm, st);

@@ -71,6 +71,23 @@ def test_page_shapes_vs_exact_kernel(evdr, cuda, lp, npg, varlen):
     U.assert_scores_close(got.cpu().numpy(), ref.cpu().numpy())
 
 
+@pytest.mark.parametrize("lp,npg,varlen,nq", [(64, 3000, False, 64), (64, 2000, True, 128), (16, 5000, False, 48),
+                                               (333, 700, True, 64), (208, 900, False, 16), (1, 300, False, 32)])
+def test_short_pages_on_cta_pairs_vs_exact_kernel(evdr, cuda, lp, npg, varlen, nq, monkeypatch):
+    """Query-tile counts that fill the four slots of a CTA pair on pages shorter than two tiles: cta_group::2 with
+    the short-page (end-mask + staged-sum) epilogue -- the default there -- against the exact fp32 kernel, and
+    bit-identical to the single-CTA short-page flavour."""
+    P, pm = evdr.synth.make_pages(npg, lp, seed=lp + nq, device=cuda, n_holes=min(3, lp - 1) if lp > 1 else 0,
+                                  empty_frac=0.02, min_len=1)
+    Q, qm, rel = evdr.synth.make_queries(P, pm, nq, 32, seed=lp + 2, sigma=2.0, min_len=4, drop=0.1)
+    pk = evdr.PackedPages.from_padded(P, pm, varlen=varlen)
+    got = pk.score(Q, qm)
+    ref = evdr.score_multi_vector_masked(Q, P, qm, pm, precision="fp32")
+    U.assert_scores_close(got.cpu().numpy(), ref.cpu().numpy())
+    monkeypatch.setenv("EVDR_TC_MODE", "sp8")
+    assert torch.equal(got, pk.score(Q, qm))
+
+
 @pytest.mark.parametrize("ppi", [1, 3, 16, 1000])
 def test_work_item_sizes(evdr, cuda, ppi):
     P, pm = evdr.synth.make_pages(203, 1030, seed=77, device=cuda)
