@@ -339,9 +339,10 @@ def main():
         pk.score_packed(Qb, qm32, out=scores)                        # 1 launch  (maxsim_tc_kernel)
         e1.record()
         kernel_events.append((e0, e1))
-        return search.topk(scores, TOPK)                             # 1 launch  (topk_select_kernel); N > 1:
-                                                                     # + unpack_gathered + merge (+ NCCL's own)
-    launches_per_step = 3 if n_gpus == 1 else (4 if xmode == "peer" else 5)
+        return search.topk(scores, TOPK)                             # 1 launch  (topk_small_kernel); N > 1: + 1
+                                                                     # (merge_gathered_kernel after NCCL's own
+                                                                     #  all-gather, or exchange_merge_kernel)
+    launches_per_step = 3 if n_gpus == 1 else 4
 
     def barrier():
         if world > 1:
