@@ -196,6 +196,10 @@ def test_A7_topk_fused_into_the_scan(evdr, cuda, nq):
         assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s), (nq, k)
         ts, ti = torch.topk(full, k, dim=1)
         assert torch.equal(got_s, ts)
+    if nq in (1, 13):                                          # k > 32: scores + two-stage selection inside the same call
+        want_s, want_i = evdr.top_k(full, 50, id_offset=7000)
+        got_s, got_i = pk.search(Q, qm, 50)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
     # ragged pages, a corpus smaller than the grid, k beyond the page count
     P, pmask = evdr.synth.make_pages(37, 700, seed=5, device=cuda, n_holes=4, empty_frac=0.05, min_len=100)
     Qs, qms, _ = evdr.synth.make_queries(P, pmask, min(nq, 4), 32, seed=6, sigma=2.0)

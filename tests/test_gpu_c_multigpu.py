@@ -65,6 +65,10 @@ def _worker(rank, world, port, ret):
                 ss = evdr.ShardedSearch((ulo, uhi), mode=mode)
                 fs, fi = ss.search(ushard, Qf, qmf, k)
                 ok = ok and torch.equal(fi, ref_i) and torch.equal(fs, ref_s)
+                if nq_f in (3, 21):                             # k > 32: the unfused route through both exchanges
+                    r40_s, r40_i = evdr.top_k(whole.score(Qf, qmf), 40)
+                    f40_s, f40_i = ss.search(ushard, Qf, qmf, 40)
+                    ok = ok and torch.equal(f40_i, r40_i) and torch.equal(f40_s, r40_s)
                 if nq_f == 1:
                     gs = evdr.GraphedSearch(ss, ushard, nq_f, k)
                     for _ in range(3):
