@@ -5,28 +5,33 @@
 // (evaluator/retrieval.py:166-213 on the packed page stream, where masked slots hold
 //  duplicates of valid tokens and empty pages are zero tokens -- see pack.cu.)
 //
-// Structure: persistent, warp-specialised, one CTA per SM, 192 threads:
-//   warp 0      TMA producer  : cp.async.bulk.tensor of query tiles (A, resident) and page-token
-//                               tiles (B, STAGES-deep ring) into 128B-swizzled shared memory
-//   warp 1      MMA issuer    : one thread issues tcgen05.mma.kind::f16 (K=16 x 8 per tile), fp32
-//                               accumulators double-buffered in TMEM (2 x BN columns)
-//   warps 2..5  epilogue      : tcgen05.ld 32 columns at a time (double-buffered in registers);
-//                               lane = query token, so the max over page tokens is a per-thread
+// Structure: persistent, warp-specialised, one CTA per SM, 192 or 320 threads:
+//   warp 0      TMA producer  : draws work items from a global counter (dynamic scheduler) and publishes
+//                               them through a shared-memory ring; cp.async.bulk.tensor of query tiles (A,
+//                               resident; double-buffered in the pair flavour) and page-token tiles (B,
+//                               STAGES-deep ring) into 128B-swizzled shared memory
+//   warp 1      MMA issuer    : one thread issues tcgen05.mma.kind::f16 (K=16 x 8 per pass; x 24 for the
+//                               bf16x3 split), fp32 accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 2..   epilogue      : one group of 4 warps, or two groups (EW = 8: pass (tile, r) -> TMEM buffer r
+//                               -> group r).  tcgen05.ld 32 columns at a time (double-buffered in
+//                               registers); lane = query token, so the max over page tokens is a per-thread
 //                               FMNMX3 tree; at a page's last chunk: * qmask, warp-shuffle sum over the
-//                               32 tokens of the query, one fp32 store.  The similarity matrix never
-//                               leaves the SM.
+//                               32 tokens of the query, one fp32 store (and / or the fused top-k list).
+//                               The similarity matrix never leaves the SM.
 //
-// Two flavours of the same kernel:
-//   CG2 = false : one CTA per tile, tcgen05.mma.cta_group::1, M = 128 x N = 256.  Used for a single
-//                 query tile (<= 4 queries): the HBM-bound streaming scan.
-//   CG2 = true  : CTA pairs (cluster of 2), tcgen05.mma.cta_group::2, M = 256 x N = 256: each CTA
-//                 holds its own 128 query-token rows and HALF of the page tile, so the shared-memory
-//                 operand traffic per SM drops from 96 to 64 B/clk and the L2->SM page traffic
-//                 halves.  Used for batched scoring (tensor-bound).
+// Flavours of the same kernel (template parameters, see packed_dispatch for which runs when):
+//   CG2 = false : one CTA per tile, tcgen05.mma.cta_group::1, M = 128 x N = BN.  3-12 queries, tile counts
+//                 that would idle slots of a pair, the argmax (training) variants.
+//   CG2 = true  : CTA pairs (cluster of 2), tcgen05.mma.cta_group::2, M = 256 x N = 256: each CTA holds its
+//                 own 128 query-token rows and HALF of the page tile, so the shared-memory operand traffic
+//                 per SM drops from 96 to 64 B/clk and the L2->SM page traffic halves.  The leader CTA
+//                 issues the MMAs and draws the items for both (DSMEM ring).  THE DEFAULT for batched
+//                 scoring (>= 13 queries): 1584-1614 TFLOP/s at 1024 queries x 100k pages.
+//   (one or two queries run maxsim_scan.cu, where the page tokens are the M side.)
 //
-// Work item = (page block pb, query group g): R resident A tiles per CTA x all B tiles of the block.
-// Items are ordered g-fastest and dealt round-robin to CTAs (pairs) so that concurrently running
-// CTAs read the same page block (L2 hit) and HBM sees every page about once.
+// Work item = (page block pb, query group g): the group's resident A tiles x all B tiles of the block.
+// Items are ordered g-fastest and handed out dynamically, so that concurrently running CTAs read the
+// same page block (L2 hit) and HBM sees every page about once (DRAM traffic 1.07x algorithmic).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -156,7 +161,6 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = CG2 ? (int)cluster_ctarank() : 0;            // 0 = leader of the CTA pair
-  const int unit = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_units = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
