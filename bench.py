@@ -168,7 +168,7 @@ def reference_sample(device="cpu"):
             torch.ones(REF_P, LP_VALID, dtype=torch.bool, device=device))
 
 
-def cpu_reference_rate(steps: int = 3, warmup: int = 1):
+def cpu_reference_rate(steps: int = 8, warmup: int = 1):
     """The reference's CPU path on the box's host cores: `steps` timed passes over the fixed sample."""
     import torch
     fn, kind = reference_scorer()
