@@ -775,7 +775,13 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   // one or two queries: the operand-swapped streaming scan (maxsim_scan.cu: page tokens on the M side, 4x / 2x
   // fewer tensor cycles per byte -- the scan is power-bound as well as HBM-bound).  EVDR_TC_MODE=scan forces
   // it, any other mode keeps the query-major kernels below.
-  if (nq <= 2 && !argmax && k_blocks == 1 && (!mode || strcmp(mode, "scan") == 0)) {
+  // By page length (profiles/r2_scan_page_lengths.log, GB/s of page bytes for one / two queries): the lean
+  // running-max epilogue of the swapped kernel wins from ~160 / ~400 tokens per page on (7.3-7.5 vs 6.8 TB/s),
+  // its short-page epilogue below ~48 tokens (2.9 vs 1.8 TB/s at 16-token pages), and in between the
+  // query-major R = 1 kernel below is as good or better (5.4 TB/s at 64 tokens, 6.8 at 128).
+  const double scan_avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
+  const bool scan_len_ok = scan_avg_tok < 48.0 || scan_avg_tok >= (nq == 1 ? 160.0 : 400.0);
+  if (nq <= 2 && !argmax && k_blocks == 1 && ((!mode && scan_len_ok) || (mode && strcmp(mode, "scan") == 0))) {
     if (tk && tk->k > 32) return EVDR_ERR_UNSUPPORTED;
     return scan_swapped(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, pages_per_item, out,
                         out_ld, tk ? tk->k : 0, tk ? tk->id_offset : 0, tk ? tk->cand_s : nullptr,
