@@ -26,6 +26,7 @@ namespace evdr {
 using namespace ptx;
 
 constexpr int SCAN_TM = 128;                         // page tokens per MMA / per ring stage
+constexpr int SCAN_STAGES = 6;                       // 6 x 32 KB ring
 constexpr int SCAN_STAGE_BYTES = SCAN_TM * EVDR_TC_DIM * 2;
 constexpr int SCAN_HALF_BYTES = SCAN_TM * 64 * 2;    // one 64-wide K sub-tile of a stage
 constexpr int SCAN_NBUF = 4;                         // TMEM accumulator buffers of 128 columns each
@@ -55,41 +56,26 @@ __device__ __forceinline__ void epi_bar_sync() {      // the 128 epilogue thread
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
-// SHORTP ("short pages"): epilogue for corpora whose pages are shorter than about two tiles, where the page-end
-// work (not the tile work) dominates.  Every warp transposes its 32 x 32 block of similarities through shared
-// memory (lane = page token -> lane = query token), reduces it to the per-token maxes of its two 16-token chunks
-// and publishes them; after ONE named barrier per tile the query's finishing warp folds the tile's eight chunk
-// maxes into its running per-token max exactly like the query-major epilogue -- page ends come from a
-// redux.or "chunk closes a page" mask, a finished page costs one shuffle sum and one store.  The cost per
-// tile no longer depends on how many pages end in it (the plain epilogue pays 32 redux.sync + a barrier per
-// page end: fine at 8 tiles per page, 2x too slow at 2 pages per tile).
-template <int NQ, bool SHORTP = false>
+template <int NQ>
 struct ScanCfg {
-  static constexpr int STAGES = SHORTP ? 5 : 6;                  // ring of 32 KB page tiles
   static constexpr int N = 32 * NQ;                              // MMA N = query tokens
   static constexpr int Q_HALF_BYTES = N * 64 * 2;
   static constexpr int Q_BYTES = 2 * Q_HALF_BYTES;               // 8 KB per query
   static constexpr int Q_ALLOC = ((Q_BYTES + 1023) / 1024) * 1024;
-  static constexpr int P_BYTES = STAGES * SCAN_STAGE_BYTES;
+  static constexpr int P_BYTES = SCAN_STAGES * SCAN_STAGE_BYTES;
   static constexpr int BAR_OFF = Q_ALLOC + P_BYTES;
   // full[S], empty[S], q_full, t_full[NBUF], t_empty[NBUF], tmem ptr, slot_full[NSLOT], slot_empty[NSLOT], items
-  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 1 + 2 * SCAN_NBUF) + 8 + 8 * 2 * SCAN_NSLOT + 4 * SCAN_NSLOT;
+  static constexpr int BAR_BYTES = 8 * (2 * SCAN_STAGES + 1 + 2 * SCAN_NBUF) + 8 + 8 * 2 * SCAN_NSLOT + 4 * SCAN_NSLOT;
   static constexpr int XW_OFF = BAR_OFF + ((BAR_BYTES + 15) / 16) * 16;
-  static constexpr int XW_BYTES = (SHORTP ? 2 : 1) * 2 * 4 * NQ * 32 * 4;   // [parity][warp][query][token] | SHORTP: [parity][query][8 chunks][token]
-  // SHORTP: [parity][query][8 chunks][32 tokens] chunk maxes (same size as XW: 8 = 4 warps x 2) and the
-  // per-warp transpose scratch, 32 rows of 36 floats
-  static constexpr int TW_PITCH = 36;
-  static constexpr int TW_OFF = XW_OFF + XW_BYTES;
-  static constexpr int TW_BYTES = SHORTP ? 4 * 32 * TW_PITCH * 4 : 0;
-  static constexpr int TOTAL = TW_OFF + TW_BYTES + 1024;
+  static constexpr int XW_BYTES = 2 * 4 * NQ * 32 * 4;           // [parity][warp][query][token]
+  static constexpr int TOTAL = XW_OFF + XW_BYTES + 1024;
 };
 
-template <int NQ, bool SHORTP = false>
+template <int NQ>
 __global__ void __launch_bounds__(192, 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapP,
                    const ScanParams prm) {
-  using S = ScanCfg<NQ, SHORTP>;
-  constexpr int SCAN_STAGES = S::STAGES;
+  using S = ScanCfg<NQ>;
   constexpr uint32_t IDESC = make_idesc_bf16(SCAN_TM, S::N);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -224,8 +210,6 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_const
         return (pp < p1) ? (prm.chunk_off[pp + 1] - c0) : 0x7fffffff;
       };
       int pe_cache = load_pe(0);
-      int pe_next = SHORTP ? load_pe(1) : 0;             // SHORTP: the next batch of 32 page ends as well
-      float rms = -INFINITY;                             // SHORTP: running max of query token `lane` (finishing warp)
       int p = p0;
       int pe = __shfl_sync(0xffffffffu, pe_cache, 0);
       float rm[NQ][32];
@@ -249,66 +233,6 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_t_empty(buf));
 
-        if constexpr (SHORTP) {
-          // ---- transpose this warp's 32 page tokens x 32 query tokens; per-token maxes of its two chunks
-          float* tw = reinterpret_cast<float*>(smem_al + S::TW_OFF) + quad * (32 * S::TW_PITCH);
-          float* cmx = xw + (tile_it & 1) * (NQ * SCAN_CH * 32);        // [query][chunk][token]
-#pragma unroll
-          for (int q = 0; q < NQ; ++q) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(tw + lane * S::TW_PITCH + 4 * i) =
-                  make_float4(v[q][4 * i], v[q][4 * i + 1], v[q][4 * i + 2], v[q][4 * i + 3]);
-            __syncwarp();
-            float c[32];
-#pragma unroll
-            for (int t = 0; t < 32; ++t) c[t] = tw[t * S::TW_PITCH + lane];
-            __syncwarp();
-            float m0 = max3(c[0], c[1], c[2]), m1 = max3(c[16], c[17], c[18]);
-#pragma unroll
-            for (int t = 3; t + 1 < 16; t += 2) { m0 = max3(m0, c[t], c[t + 1]); m1 = max3(m1, c[16 + t], c[17 + t]); }
-            m0 = fmaxf(m0, c[15]);
-            m1 = fmaxf(m1, c[31]);
-            cmx[(q * SCAN_CH + 2 * quad) * 32 + lane] = m0;
-            cmx[(q * SCAN_CH + 2 * quad + 1) * 32 + lane] = m1;
-          }
-          epi_bar_sync();
-          if (quad < NQ && quad < prm.nq) {                  // warp q walks the tile's chunks for query q
-            const int q = quad;
-            float w = qm[0];
-#pragma unroll
-            for (int j = 1; j < NQ; ++j) w = (q == j) ? qm[j] : w;
-            auto end_bit = [&](int pev) {
-              const int pos = pev - ch0 - 1;
-              return (pos >= 0 && pos < SCAN_CH) ? (1u << pos) : 0u;
-            };
-            const unsigned endmask = __reduce_or_sync(0xffffffffu, end_bit(pe_cache) | end_bit(pe_next));
-#pragma unroll
-            for (int j = 0; j < SCAN_CH; ++j) {
-              rms = fmaxf(rms, cmx[(q * SCAN_CH + j) * 32 + lane]);
-              if (endmask & (1u << j)) {                     // warp-uniform: chunk j closes page p
-                const float sc = warp_sum(rms * w);
-                if (prm.out != nullptr && lane == 0) prm.out[(size_t)q * prm.out_ld + p] = sc;
-                if (prm.tk_k > 0 && sc > tk_thr) {
-                  const int pos = __popc(__ballot_sync(0xffffffffu, tk_s >= sc));
-                  const float us = __shfl_up_sync(0xffffffffu, tk_s, 1);
-                  const int up = __shfl_up_sync(0xffffffffu, tk_p, 1);
-                  if (lane == pos) { tk_s = sc; tk_p = p; }
-                  else if (lane > pos) { tk_s = us; tk_p = up; }
-                  tk_thr = __shfl_sync(0xffffffffu, tk_s, prm.tk_k - 1);
-                }
-                rms = -INFINITY;
-                ++p;
-              }
-            }
-            const int b = (p - p0) >> 5;
-            if (b != cb) {
-              pe_cache = (b == cb + 1) ? pe_next : load_pe(b);
-              pe_next = load_pe(b + 1);
-              cb = b;
-            }
-          }
-        } else {
         int lo = 0;                                         // chunks of this tile below `lo` are consumed
         while (pe - ch0 <= SCAN_CH) {                       // page p ends inside (or at the end of) this tile
           const int e = pe - ch0;
@@ -370,7 +294,6 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_const
 #pragma unroll
             for (int n = 0; n < 32; ++n) rm[q][n] = in ? fmaxf(rm[q][n], v[q][n]) : rm[q][n];
         }
-        }  // !SHORTP
       }
     }
     if (prm.tk_k > 0 && quad < NQ && quad < prm.nq && lane < prm.tk_k) {
@@ -403,16 +326,16 @@ static int encode_2d(evdr_handle* h, CUtensorMap* tm, const void* base, uint64_t
   return EVDR_OK;
 }
 
-template <int NQ, bool SHORTP>
+template <int NQ>
 static int launch_scan(evdr_handle* h, const void* Qb, const void* tokens, int64_t n_tokens, ScanParams prm,
                        int grid, cudaStream_t st) {
-  using S = ScanCfg<NQ, SHORTP>;
+  using S = ScanCfg<NQ>;
   CUtensorMap tmQ, tmP;
   int rc = encode_2d(h, &tmQ, Qb, (uint64_t)prm.nq * EVDR_TC_LQ, S::N, "queries");
   if (rc != EVDR_OK) return rc;
   rc = encode_2d(h, &tmP, tokens, (uint64_t)n_tokens, SCAN_TM, "page tokens");
   if (rc != EVDR_OK) return rc;
-  auto kern = maxsim_scan_kernel<NQ, SHORTP>;
+  auto kern = maxsim_scan_kernel<NQ>;
   if ((size_t)S::TOTAL > h->smem_optin)
     return set_error(EVDR_ERR_UNSUPPORTED, "scan kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -459,16 +382,8 @@ int scan_swapped(evdr_handle* h, const void* Qb, const uint8_t* qmask32, int nq,
   prm.n_items = (np + ppi - 1) / ppi;
   const int grid = prm.n_items < h->sm_count ? prm.n_items : h->sm_count;
   if (n_cta) *n_cta = grid;
-  // short pages take the short-page epilogue (cost per tile independent of the number of page ends in it), longer
-  // pages the leaner running-max epilogue; the caller (packed_dispatch) sends the middle lengths, where neither
-  // wins, to the query-major kernel
-  const double avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
-  const char* force = getenv("EVDR_SCAN_EPILOGUE");             // "short" | "long": A/B runs
-  const bool shortp = force ? strcmp(force, "short") == 0 : avg_tok < 100.0;
-  if (nq == 1) return shortp ? launch_scan<1, true>(h, Qb, tokens, n_tokens, prm, grid, st)
-                             : launch_scan<1, false>(h, Qb, tokens, n_tokens, prm, grid, st);
-  return shortp ? launch_scan<2, true>(h, Qb, tokens, n_tokens, prm, grid, st)
-                : launch_scan<2, false>(h, Qb, tokens, n_tokens, prm, grid, st);
+  if (nq == 1) return launch_scan<1>(h, Qb, tokens, n_tokens, prm, grid, st);
+  return launch_scan<2>(h, Qb, tokens, n_tokens, prm, grid, st);
 }
 
 }  // namespace evdr

@@ -131,7 +131,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert((BN / 32) % 2 == 0, "the drain loop handles 32-column groups in pairs");
   static_assert(EW == 4 || (EW == 8 && R == 2), "8 epilogue warps need R == 2");
-  static_assert(!TK || (!CG2 && !AM && !SP && KB == 1), "fused top-k: single-CTA bf16 scoring flavours, long-page epilogue");
+  static_assert(!TK || (!CG2 && !AM && KB == 1), "fused top-k: single-CTA bf16 scoring flavours");
   constexpr uint32_t IDESC = make_idesc_bf16(CG2 ? 256 : 128, BN);
   constexpr int CH_PER_TILE = BN / EVDR_CHUNK;
 
@@ -354,6 +354,18 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
     int tk_p[TK ? R : 1];
 #pragma unroll
     for (int r = 0; r < (TK ? R : 1); ++r) { tk_s[r] = -INFINITY; tk_thr[r] = -INFINITY; tk_p[r] = -1; }
+    // pages arrive in ascending order within a CTA (items are drawn from an increasing counter), so an equal
+    // score never displaces an entry: strict '>' keeps (score desc, page asc).  `s` is warp-uniform.
+    auto tk_insert = [&](float& ls, int& lp, float& thr, float s, int page) {
+      if (s > thr) {
+        const int pos = __popc(__ballot_sync(0xffffffffu, ls >= s));
+        const float us = __shfl_up_sync(0xffffffffu, ls, 1);
+        const int up = __shfl_up_sync(0xffffffffu, lp, 1);
+        if (lane == pos) { ls = s; lp = page; }
+        else if (lane > pos) { ls = us; lp = up; }
+        thr = __shfl_sync(0xffffffffu, ls, prm.tk_k - 1);
+      }
+    };
     const uint32_t t_empty0 = CG2 ? mapa_u32(bar_t_empty(0), 0) : bar_t_empty(0);
     const uint32_t t_empty1 = CG2 ? mapa_u32(bar_t_empty(1), 0) : bar_t_empty(1);
     auto release_tmem = [&](int buf) {
@@ -510,16 +522,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                 const float s = warp_sum(rm * qm[r]);        // every lane holds the sum
                 if constexpr (TK) {
                   if (prm.out != nullptr && lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
-                  // pages arrive in ascending order within a CTA (items are drawn from an increasing counter),
-                  // so an equal score never displaces an entry: strict '>' keeps (score desc, page asc)
-                  if (s > tk_thr[r]) {
-                    const int pos = __popc(__ballot_sync(0xffffffffu, tk_s[r] >= s));
-                    const float us = __shfl_up_sync(0xffffffffu, tk_s[r], 1);
-                    const int up = __shfl_up_sync(0xffffffffu, tk_p[r], 1);
-                    if (lane == pos) { tk_s[r] = s; tk_p[r] = p; }
-                    else if (lane > pos) { tk_s[r] = us; tk_p[r] = up; }
-                    tk_thr[r] = __shfl_sync(0xffffffffu, tk_s[r], prm.tk_k - 1);
-                  }
+                  tk_insert(tk_s[r], tk_p[r], tk_thr[r], s, p);
                 } else {
                   if (lane == 0 && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p] = s;
                 }
@@ -587,11 +590,15 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_constan
                 // 32-token sums of the k finished pages: lane l adds up row l (conflict-free thanks to
                 // the 33-float row pitch), then k lanes store k consecutive scores at once
                 __syncwarp();
+                float sacc = 0.f;
                 if (lane < k) {
-                  float sacc = 0.f;
 #pragma unroll
                   for (int t = 0; t < 32; ++t) sacc += stg[lane * S::STG_ROW + t];
-                  if (qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p + lane] = sacc;
+                  if ((!TK || prm.out != nullptr) && qidx[r] >= 0) prm.out[(size_t)qidx[r] * prm.out_ld + p + lane] = sacc;
+                }
+                if constexpr (TK) {                   // the k finished pages, in page order, into the register list
+                  for (int i = 0; i < k; ++i)
+                    tk_insert(tk_s[r], tk_p[r], tk_thr[r], __shfl_sync(0xffffffffu, sacc, i), p + i);
                 }
                 __syncwarp();
                 p += k;
@@ -775,12 +782,12 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   // one or two queries: the operand-swapped streaming scan (maxsim_scan.cu: page tokens on the M side, 4x / 2x
   // fewer tensor cycles per byte -- the scan is power-bound as well as HBM-bound).  EVDR_TC_MODE=scan forces
   // it, any other mode keeps the query-major kernels below.
-  // By page length (profiles/r2_scan_page_lengths.log, GB/s of page bytes for one / two queries): the lean
-  // running-max epilogue of the swapped kernel wins from ~160 / ~400 tokens per page on (7.3-7.5 vs 6.8 TB/s),
-  // its short-page epilogue below ~48 tokens (2.9 vs 1.8 TB/s at 16-token pages), and in between the
-  // query-major R = 1 kernel below is as good or better (5.4 TB/s at 64 tokens, 6.8 at 128).
+  // By page length (profiles/r2_scan_page_lengths.log, r2_short_pages_one_tile.log; GB/s of page bytes): the
+  // operand-swapped kernel wins from ~160 (one query) / ~400 (two queries) tokens per page on (7.3-7.5 vs 6.8
+  // TB/s); shorter pages take the query-major kernel with the short-page epilogue below (6.4-6.5 TB/s down to
+  // 16-token pages, where per-page work would otherwise dominate: 1.8 TB/s with the long-page epilogue).
   const double scan_avg_tok = (double)total_chunks * EVDR_CHUNK / (double)np;
-  const bool scan_len_ok = scan_avg_tok < 48.0 || scan_avg_tok >= (nq == 1 ? 160.0 : 400.0);
+  const bool scan_len_ok = scan_avg_tok >= (nq == 1 ? 160.0 : 400.0);
   if (nq <= 2 && !argmax && k_blocks == 1 && ((!mode && scan_len_ok) || (mode && strcmp(mode, "scan") == 0))) {
     if (tk && tk->k > 32) return EVDR_ERR_UNSUPPORTED;
     return scan_swapped(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, pages_per_item, out,
@@ -828,6 +835,10 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   const double avg_chunks = (double)total_chunks / (double)np;
   const bool force_sp8 = mode && strcmp(mode, "sp8") == 0;
   const bool short_pages = two_groups_ok && prm.nqt >= 2 && (avg_chunks < 32.0 || force_sp8);
+  // one query tile (<= 4 queries) on short pages: the short-page epilogue with one epilogue group ("sp4")
+  const bool one_tile_sp = !pair && !argmax && k_blocks == 1 && prm.nqt == 1 &&
+                           ((mode && strcmp(mode, "sp4") == 0) ||
+                            (!mode && scan_avg_tok < (nq == 1 ? 160.0 : nq == 2 ? 400.0 : 512.0)));
   const bool want_ew8 = two_groups_ok && !short_pages &&
                         (prm.nqt >= 16 || (mode && strcmp(mode, "ew8") == 0 && prm.nqt >= 2));
   // Query tiles in TMEM + a 4-stage ring of 192-token page tiles: the default for exactly two query tiles
@@ -898,6 +909,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
     prm.tk_k = tk->k;
     prm.id_offset = tk->id_offset;
     if (ta2) return launch_tc<2, 192, 4, false, false, 1, false, 8, true, true>(h, Qb, tokens, n_tokens, prm, st);
+    if (one_tile_sp) return launch_tc<1, 256, 2, false, false, 1, true, 4, false, true>(h, Qb, tokens, n_tokens, prm, st);
     return launch_tc<1, 256, 3, false, false, 1, false, 4, false, true>(h, Qb, tokens, n_tokens, prm, st);
   }
   if (k_blocks == 3) {
@@ -921,6 +933,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   }
   if (short_pages) return launch_tc<2, 256, 2, false, false, 1, true, 8>(h, Qb, tokens, n_tokens, prm, st);
   if (want_ew8) return launch_tc<2, 256, 2, false, false, 1, false, 8>(h, Qb, tokens, n_tokens, prm, st);
+  if (one_tile_sp) return launch_tc<1, 256, 2, false, false, 1, true, 4>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 1) return launch_tc<1, 256, 3, false>(h, Qb, tokens, n_tokens, prm, st);
   if (R == 2) return launch_tc<2, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);
   return launch_tc<3, 256, 2, false>(h, Qb, tokens, n_tokens, prm, st);

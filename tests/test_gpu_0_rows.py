@@ -207,6 +207,17 @@ def test_A7_topk_fused_into_the_scan(evdr, cuda, nq):
     want_s, want_i = evdr.top_k(pks.score(Qs, qms), 32)
     got_s, got_i = pks.search(Qs, qms, 32)
     assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+    # compressed 64- and 16-token pages (several page ends per tile: the short-page epilogue feeds the list)
+    for lp_c, n_c in ((64, 9000), (16, 20000)):
+        Pc, pmc = evdr.synth.make_pages(n_c, lp_c, seed=lp_c, device=cuda, n_holes=2, empty_frac=0.01, min_len=lp_c // 2)
+        Pc[4000:4005] = Pc[11:16]
+        pmc[4000:4005] = pmc[11:16]                              # duplicated pages: ties by page id
+        Qc, qmc, _ = evdr.synth.make_queries(Pc, pmc, min(nq, 4), 32, seed=lp_c + 1, sigma=1.5, min_len=8, drop=0.1)
+        for varlen in (False, True):
+            pkc = evdr.PackedPages.from_padded(Pc, pmc, varlen=varlen, page_offset=50)
+            want_s, want_i = evdr.top_k(pkc.score(Qc, qmc), 10, id_offset=50)
+            got_s, got_i = pkc.search(Qc, qmc, 10)
+            assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s), (lp_c, varlen)
     small = evdr.PackedPages.from_padded(P[:5], pmask[:5], varlen=True)
     got_s, got_i = small.search(Qs, qms, 10)
     assert (got_i[:, 5:] == -1).all() and torch.isinf(got_s[:, 5:]).all()
