@@ -591,18 +591,19 @@ int evdr_sharded_search(evdr_handle* h, const void* Qb, const uint8_t* qmask32, 
   EVDR_CHECK_ARG(k >= 1 && k <= 128, "evdr_sharded_search: k=%d outside [1,128]", k);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool solo = exchange == 0 || (exchange == 1 && h->world == 1 && !h->nccl_comm);
-  // per-CTA candidate lists of the fused scan (k <= 32) ...
+  // per-CTA candidate lists of the fused scan (one query group: at most 8 queries, k <= 32) ...
   const int max_cta = h->sm_count;
   unsigned char* ws = nullptr;
-  const size_t cand_n = (size_t)nq * max_cta * (k <= 32 ? k : 0);
+  const bool try_fused = nq <= 8 && k <= 32;
+  const size_t cand_n = try_fused ? (size_t)nq * max_cta * k : 0;
   const size_t row_bytes = sizeof(float) * (size_t)nq * np;     // ... or the score rows of the unfused route
   EVDR_CUDA(ws_alloc(h, &ws, cand_n * 12 + 64, st));
   long long* cand_i = reinterpret_cast<long long*>(ws);
   float* cand_s = reinterpret_cast<float*>(ws + cand_n * 8);
   int n_cta = 0;
-  int rc = k <= 32 ? scan_topk(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, k, id_offset,
-                               cand_s, cand_i, &n_cta, st)
-                   : EVDR_ERR_UNSUPPORTED;
+  int rc = try_fused ? scan_topk(h, Qb, qmask32, nq, tokens, n_tokens, chunk_off, np, total_chunks, k, id_offset,
+                                 cand_s, cand_i, &n_cta, st)
+                     : EVDR_ERR_UNSUPPORTED;
   if (rc == EVDR_OK) {
     const int ncand = n_cta * k;
     if (solo) rc = select_candidates(h, cand_s, cand_i, nq, ncand, k, top_scores, reinterpret_cast<long long*>(top_ids), st);

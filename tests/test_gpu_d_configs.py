@@ -33,6 +33,25 @@ def test_comparator_is_the_unmodified_reference():
     assert "baseline/_ref/evaluator/retrieval.py" in fn.__code__.co_filename.replace("\\", "/")
 
 
+@pytest.mark.parametrize("dtype,batch_size", [(torch.float32, 128), (torch.float32, 7), (torch.bfloat16, 16)])
+def test_A2_list_scorer_vs_the_reference_on_this_gpu(evdr, cuda, dtype, batch_size, capsys):
+    """A2 against the reference's OWN BaseVisualRetrieverProcessor.score_multi_vector (evaluator/retrieval.py:101-150,
+    left_padding :30-45 hard-codes 'cuda', so it can only run on the GPU box): lists of ragged (Li, 128) tensors,
+    blocks of batch_size zero-LEFT-padded pages whose zero tokens take part in the max."""
+    if not reference.available():
+        pytest.skip(reference.why_unavailable())
+    g = torch.Generator().manual_seed(batch_size)
+    qs = [torch.nn.functional.normalize(torch.randn(int(n), 128, generator=g), dim=-1).to(dtype)
+          for n in torch.randint(3, 33, (21,), generator=g)]
+    ps = [torch.nn.functional.normalize(torch.randn(int(n), 128, generator=g), dim=-1).to(dtype)
+          for n in torch.randint(1, 300, (45,), generator=g)]
+    want = reference.scorer_module().BaseVisualRetrieverProcessor.score_multi_vector(qs, ps, batch_size=batch_size, device="cuda")
+    capsys.readouterr()                                           # the reference prints its timings
+    got = evdr.BaseVisualRetrieverProcessor.score_multi_vector(qs, ps, batch_size=batch_size, device=str(cuda))
+    assert got.device.type == "cpu" and got.dtype == torch.float32 and got.shape == want.shape == (21, 45)
+    U.assert_scores_close(got.numpy(), want.numpy(), rel=2e-5 if dtype == torch.float32 else U.REL_TOL)
+
+
 def _torch_maxsim_restated(Q, P, qmask, pmask, chunk=32):
     """Plain torch fp32 MaxSim with the reference's semantics (evaluator/retrieval.py:166-213),
     written for the tests: one matmul per page chunk, -1e4 fill, max, has-token and query masks, sum."""
