@@ -184,3 +184,36 @@ def test_dropin_criterion_module_exports_the_reference_names(evdr, cuda):
         assert loss.shape == () and bool(torch.isfinite(loss))
         loss.backward()
     assert bool(torch.isfinite(s.grad).all())
+
+
+@pytest.mark.parametrize("B,N,k,T", [(32, 500, 10, 1.0), (32, 1000, 40, 0.1), (7, 70, 40, 0.5)])
+def test_losses_vs_the_reference_criterion_on_this_gpu(evdr, cuda, B, N, k, T):
+    """All seven losses and their gradients against the reference's OWN criterion.py (unmodified file staged in
+    baseline/_ref) evaluated with torch autograd on the same GPU, at MaxSim score magnitudes."""
+    from baseline import ref as reference
+    if not reference.available():
+        pytest.skip(reference.why_unavailable())
+    crit = reference.criterion_module()
+    g = torch.Generator().manual_seed(B * N)
+    t = (14.0 + 2.5 * torch.randn(B, N, generator=g)).to(cuda)
+    s0 = (t.cpu() + 1.0 * torch.randn(B, N, generator=g)).to(cuda)
+    labels = torch.randint(0, N, (B,), generator=g).to(cuda)
+    cases = [("listwise", lambda m, x: m.listwise_distillation_loss(x, t, k=k, temperature=T)),
+             ("score_preserving", lambda m, x: m.score_preserving_loss(x, t)),
+             ("pairwise", lambda m, x: m.pairwise_distillation_loss(x, t)),
+             ("ranknce", lambda m, x: m.ranknce_loss(x, t, temperature=T, lambda_weight=0.7)),
+             ("infonce_distillation", lambda m, x: m.infonce_distillation_loss(x, t, temperature=0.07)),
+             ("infonce_supervised", lambda m, x: m.infonce_supervised_loss(x, labels, temperature=0.07)),
+             ("lambda", lambda m, x: m.lambda_loss(x, t))]
+    for name, fn in cases:
+        xs, xr = s0.clone().requires_grad_(True), s0.clone().requires_grad_(True)
+        lo_, lr_ = fn(evdr, xs), fn(crit, xr)
+        lo_.backward()
+        lr_.backward()
+        gr = xr.grad.cpu().numpy()
+        if name == "lambda":      # quantised sigmoid differences (see test_losses_match_reference)
+            np.testing.assert_allclose(lo_.item(), lr_.item(), rtol=1e-3, err_msg=name)
+            np.testing.assert_allclose(xs.grad.cpu().numpy(), gr, rtol=1e-2, atol=1e-3 * np.abs(gr).max(), err_msg=name)
+        else:
+            np.testing.assert_allclose(lo_.item(), lr_.item(), rtol=5e-5, atol=1e-7, err_msg=name)
+            np.testing.assert_allclose(xs.grad.cpu().numpy(), gr, rtol=1e-3, atol=5e-6 * max(np.abs(gr).max(), 1e-30), err_msg=name)
