@@ -211,8 +211,17 @@ class GraphedSearch:
             body()
 
     def __call__(self, Q: torch.Tensor, qmask: torch.Tensor):
-        self.Q.copy_(Q, non_blocking=True)
-        self.qmask.copy_(qmask, non_blocking=True)
+        """Q (nq, lq <= the captured lq, 128) on the host (pinned for an asynchronous copy) or the device."""
+        nq, lq = Q.shape[0], Q.shape[1]
+        if nq != self.Q.shape[0] or lq > self.Q.shape[1] or Q.shape[2] != self.Q.shape[2]:
+            raise ValueError(f"graph captured for queries {tuple(self.Q.shape)}, got {tuple(Q.shape)}")
+        if lq == self.Q.shape[1]:
+            self.Q.copy_(Q, non_blocking=True)
+            self.qmask.copy_(qmask != 0 if qmask.dtype != torch.bool else qmask, non_blocking=True)
+        else:                                   # shorter queries: the remaining token slots are masked out
+            self.qmask.zero_()
+            self.Q[:, :lq].copy_(Q, non_blocking=True)
+            self.qmask[:, :lq].copy_(qmask != 0 if qmask.dtype != torch.bool else qmask, non_blocking=True)
         self.graph.replay()
         return self.top_s, self.top_i
 
