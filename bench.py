@@ -509,18 +509,26 @@ def check_sharded_result(torch, dist, merged, local_scores, npg, rank, world, de
     full = torch.cat(blocks, dim=1)                                  # global page id = rank * npg + local id
     ref_s, ref_i = torch.topk(full, ts.shape[1], dim=1)
     got_s, got_i = ts.index_select(0, idx), ti.index_select(0, idx)
-    if not torch.equal(got_s, ref_s):
-        return f"rank {rank}: merged top-k scores differ from torch.topk of the gathered rows"
-    tie_free = (ref_s[:, 1:] != ref_s[:, :-1]).all()
-    if bool(tie_free) and not torch.equal(got_i, ref_i):
-        return f"rank {rank}: merged top-k ids differ from torch.topk of the gathered rows"
-    if not torch.equal(full.gather(1, got_i), got_s):
-        return f"rank {rank}: merged ids do not address the merged scores"
+    # every rank takes part in BOTH collectives whatever it found locally (an early return would leave the
+    # other ranks waiting in the second all-gather)
     all_i = [torch.empty_like(got_i) for _ in range(world)]
     dist.all_gather(all_i, got_i.contiguous())
-    if not all(torch.equal(a, all_i[0]) for a in all_i):
-        return f"rank {rank}: ranks disagree on the merged top-k"
-    return "ok"
+    tie_free = (ref_s[:, 1:] != ref_s[:, :-1]).all()
+    if not torch.equal(got_s, ref_s):
+        status = f"rank {rank}: merged top-k scores differ from torch.topk of the gathered rows"
+    elif bool(tie_free) and not torch.equal(got_i, ref_i):
+        status = f"rank {rank}: merged top-k ids differ from torch.topk of the gathered rows"
+    elif not torch.equal(full.gather(1, got_i.clamp_min(0)), got_s):
+        status = f"rank {rank}: merged ids do not address the merged scores"
+    elif not all(torch.equal(a, all_i[0]) for a in all_i):
+        status = f"rank {rank}: ranks disagree on the merged top-k"
+    else:
+        status = "ok"
+    bad = torch.tensor([0 if status == "ok" else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)                      # rank 0 prints: it must know about every rank
+    if status == "ok" and int(bad.item()) != 0:
+        status = "a peer rank failed its check"
+    return status
 
 
 def corpus_1m(evdr, torch, dist, dev, rank, n_gpus, peaks, timed, xmode="nccl", peer_ok=False, total=1_000_000):

@@ -116,3 +116,56 @@ def test_gather_score_rows_world2_gloo(n_pages):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(0) and ret.get(1)
+
+
+def _check_worker(rank, world, port, ret):
+    """bench.py's self-check at N > 1 (check_sharded_result) on a gloo group: accepts the correct merged top-k,
+    rejects wrong ids, wrong scores and a rank that disagrees."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        import evdr_b200 as evdr
+        npg, k = 50, 10
+        scores = torch.randn(9, npg * world, generator=torch.Generator().manual_seed(5))
+        lo, hi = rank * npg, (rank + 1) * npg
+        local = scores[:, lo:hi].contiguous()
+        ss = evdr.ShardedSearch((lo, hi), mode="torchdist", local_topk=_cpu_topk, merge=_cpu_merge)
+        vals, ids = ss.topk(local, k)
+        dev = torch.device("cpu")
+        ok = bench.check_sharded_result(torch, dist, (vals, ids), local, npg, rank, world, dev) == "ok"
+        bad_ids = ids.clone()
+        bad_ids[0, 0] = (bad_ids[0, 0] + 1) % (npg * world)
+        ok = ok and bench.check_sharded_result(torch, dist, (vals, bad_ids), local, npg, rank, world, dev) != "ok"
+        ok = ok and bench.check_sharded_result(torch, dist, (vals + 1.0, ids), local, npg, rank, world, dev) != "ok"
+        if rank == 1:                                   # only one rank holds a different (self-consistent) answer
+            swapped = ids.clone()
+            swapped[-1, [0, 1]] = swapped[-1, [1, 0]]
+            sv = vals.clone()
+            sv[-1, [0, 1]] = sv[-1, [1, 0]]
+            res = bench.check_sharded_result(torch, dist, (sv, swapped), local, npg, rank, world, dev)
+        else:
+            res = bench.check_sharded_result(torch, dist, (vals, ids), local, npg, rank, world, dev)
+        ok = ok and res != "ok"                         # rank 1: its own answer is wrong; rank 0: the ranks disagree
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_sharded_check_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_check_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(0) and ret.get(1)
