@@ -108,6 +108,62 @@ def test_sharded_search_nccl():
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
+def _timeout_worker(rank, world, port, ret):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EVDR_PEER_TIMEOUT_MS="300")
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import evdr_b200 as evdr
+        evdr.init_nccl_comm(dev)
+        evdr.init_peer_exchange(dev, max_candidates=64 * 16)
+        lo, hi = evdr.partition_pages(400, world)[rank]
+        s = torch.randn(3, hi - lo, generator=torch.Generator().manual_seed(rank)).to(dev)
+        peer = evdr.ShardedSearch((lo, hi), mode="peer")
+        ok = True
+        if rank == 0:
+            # rank 1 never makes this call: the wait is bounded, the kernel completes with padding instead of
+            # trapping, and the NEXT peer call on this handle reports the failure
+            top_s, top_i = peer.topk(s, 5)
+            torch.cuda.synchronize(dev)
+            ok = ok and bool((top_i == -1).all()) and bool(torch.isinf(top_s).all())
+            try:
+                peer.topk(s, 5)
+                ok = False
+            except evdr._lib.EvdrError as e:
+                ok = ok and "timed out" in str(e)
+        dist.barrier()
+        # the process and the context are alive: the NCCL exchange still works on both ranks
+        ns, ni = evdr.ShardedSearch((lo, hi), mode="nccl").topk(s, 5)
+        full = [torch.empty_like(s) for _ in range(world)]
+        dist.all_gather(full, s)
+        ws, wi = evdr.top_k(torch.cat(full, dim=1), 5)
+        ok = ok and torch.equal(ni, wi) and torch.equal(ns, ws)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_peer_exchange_timeout_is_reported_not_trapped():
+    """a rank that never arrives must not kill the others' CUDA context."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(200)
+        assert p.exitcode == 0
+    assert ret.get(0) and ret.get(1), dict(ret)
+
+
 def test_peer_exchange_single_rank(evdr, cuda):
     """world = 1: the exchange kernel pushes into its own region, waits on its own flags and merges --
     the result must equal evdr_topk, including (-inf, -1) padding when k exceeds the page count."""
