@@ -69,6 +69,9 @@ struct evdr_handle {
   // stream-ordered scratch comes from a pool OWNED by the handle (the device's default pool and its
   // release threshold, which other libraries in the process may rely on, are left alone)
   cudaMemPool_t pool;
+  // cta_group::2 flavours need clusters of two CTAs with ~224 KB of shared memory each to be schedulable
+  // (not under every MPS / partitioning setup): 0 = not probed yet, 1 = yes, -1 = no (single-CTA flavours only)
+  int pair_state;
   // multi-GPU
   void* nccl_comm;  // ncclComm_t
   int rank, world;

@@ -741,6 +741,32 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
 
 using namespace evdr;
 
+// Can this device / context co-schedule clusters of two CTAs of the pair flavour?  Probed once per handle with
+// cudaOccupancyMaxActiveClusters; when it cannot, the dispatch silently stays on the single-CTA flavours.
+static bool pairs_schedulable(evdr_handle* h) {
+  if (h->pair_state == 0) {
+    using S = TcCfg<2, 256, 3, true, 1, false, 8, false>;
+    auto kern = maxsim_tc_kernel<2, 256, 3, true, false, 1, false, 8>;
+    int n = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(2 * (h->sm_count / 2));
+    cfg.blockDim = dim3(64 + 32 * 8);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    h->pair_state = (e == cudaSuccess && n >= 1) ? 1 : -1;
+  }
+  return h->pair_state > 0;
+}
+
 // fused top-k request of a dispatch (evdr::scan_topk): candidate buffers in, CTA count out
 struct TkRequest {
   float* cand_s;
@@ -807,7 +833,8 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   const int pair_groups = (prm.nqt + 3) / 4;
   const int idle_slots = 4 * pair_groups - prm.nqt;
   const bool pair8 = (mode && strcmp(mode, "pair8") == 0) ||
-                     (!mode && prm.nqt >= EVDR_PAIR_MIN_TILES && 25 * idle_slots <= 4 * pair_groups);
+                     (!mode && prm.nqt >= EVDR_PAIR_MIN_TILES && 25 * idle_slots <= 4 * pair_groups &&
+                      pairs_schedulable(h));
   // pages shorter than two tiles on average: the pair flavour with the short-page (end-mask + staged-sum)
   // epilogue -- 1560 vs 1464 TFLOP/s on 64-token pages at 1024 queries (profiles/r2_short_pages_pair.log)
   const bool pair_sp = pair8 && avg_chunks_all < 32.0;
@@ -816,7 +843,7 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   // per page tile, half a tile per CTA: 21 instead of 42 B/clk of L2 -> SM traffic per SM) unless an odd tile
   // count would idle more than ~10 % of the slots
   const bool pair_x3 = k_blocks == 3 && !argmax && prm.nqt >= 2 && (prm.nqt % 2 == 0 || prm.nqt >= 9) &&
-                       (!mode || strcmp(mode, "1cta") != 0);
+                       (!mode || strcmp(mode, "1cta") != 0) && pairs_schedulable(h);
   const bool pair = (want_pair && prm.nqt >= 2 && argmax == nullptr && k_blocks == 1) || pair_x3;
   int R, tpg;
   if (pair) { R = (prm.nqt + 1) / 2; if (R > 4) R = 4; if (pair8) R = 2; tpg = 2 * R; }
