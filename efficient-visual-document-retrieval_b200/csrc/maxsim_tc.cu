@@ -838,7 +838,11 @@ static int packed_dispatch(evdr_handle* h, const void* Qb, const uint8_t* qmask3
   // pages shorter than two tiles on average: the pair flavour with the short-page (end-mask + staged-sum)
   // epilogue -- 1560 vs 1464 TFLOP/s on 64-token pages at 1024 queries (profiles/r2_short_pages_pair.log)
   const bool pair_sp = pair8 && avg_chunks_all < 32.0;
-  const bool want_pair = (mode && strcmp(mode, "pair") == 0) || pair8;
+  // six query tiles (21-24 queries) fit ONE group of a pair with R = 3 per CTA and one epilogue group: no idle
+  // slot, no query-tile reloads, every page tile read once (1376 vs 1311 TFLOP/s, profiles/r2_pair_sweep.log)
+  const bool pair6 = !mode && prm.nqt == 6 && avg_chunks_all >= 32.0 && argmax == nullptr && k_blocks == 1 &&
+                     pairs_schedulable(h);
+  const bool want_pair = (mode && strcmp(mode, "pair") == 0) || pair8 || pair6;
   // bf16x3: one resident query tile per CTA (64 KB) and 2 x 64 KB page-tile stages; CTA pairs (2 query tiles
   // per page tile, half a tile per CTA: 21 instead of 42 B/clk of L2 -> SM traffic per SM) unless an odd tile
   // count would idle more than ~10 % of the slots
