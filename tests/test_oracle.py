@@ -147,6 +147,30 @@ def test_ndcg_cross_check_with_sklearn():
             assert abs(mine - sk) < 1e-12
 
 
+def test_map_recall_mrr_cross_check_with_sklearn():
+    """Independent implementations (scikit-learn) on tie-free, fully ranked, binary-relevance queries: average
+    precision = trec map over the whole ranking, LRAP with a single relevant page = reciprocal rank, recall@k."""
+    from sklearn.metrics import average_precision_score, label_ranking_average_precision_score
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        n = 40
+        scores = rng.standard_normal(n)
+        rel = np.zeros(n, dtype=int)
+        rel[rng.choice(n, int(rng.integers(1, 5)), replace=False)] = 1
+        docs = [f"d{i:03d}" for i in range(n)]
+        qrel = {d: 1 for d, r in zip(docs, rel) if r}
+        res = {d: float(s) for d, s in zip(docs, scores)}
+        m = to.per_query_measures(qrel, to.trec_rank(res), [5, n])
+        assert abs(m[f"map@{n}"] - average_precision_score(rel, scores)) < 1e-12
+        top5 = np.argsort(-scores)[:5]
+        assert abs(m["recall@5"] - rel[top5].sum() / rel.sum()) < 1e-12
+        single = np.zeros(n, dtype=int)
+        single[int(rng.integers(0, n))] = 1
+        qrel1 = {docs[int(single.argmax())]: 1}
+        rr = to.mrr({"q": qrel1}, {"q": res}, [n])[f"MRR@{n}"]
+        assert abs(rr - round(label_ranking_average_precision_score(single[None, :], scores[None, :]), 5)) < 1e-12
+
+
 # ----------------------------------------------------------------------------------------------
 # score-matrix consumers (criterion.py losses, rank-gap mining): oracle vs outputs of the unmodified
 # reference stored in tests/golden/losses.npz (tests/golden/make_golden_losses.py)
