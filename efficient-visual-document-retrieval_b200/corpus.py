@@ -357,3 +357,49 @@ class HostCorpus:
             out.copy_(res)
             return out
         return res
+
+    def search(self, Q: torch.Tensor, qmask: torch.Tensor, k: int = 10):
+        """Top-k pages per query over the host-resident corpus WITHOUT materialising the (nq, np) score matrix:
+        every streamed chunk goes through the one-call search (scan with the top-k in its epilogue for up to 8
+        queries), its k candidates per query are kept, and one merge over the chunks' candidates gives the result
+        (scores (nq, k) fp32, ids (nq, k) int64 global page ids).  Same overlap of copies and scoring as `score`."""
+        from .topk import topk_merge
+        if Q.shape[1] > TC_LQ or k > TOPK_MAX:
+            from .topk import topk
+            return topk(self.score(Q, qmask), k, id_offset=self.page_offset)
+        Qb, qm32 = pack_queries(Q, qmask)
+        nq = Qb.shape[0]
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        bounds, c, step = [0], 0, float(max(1, self.ppc // 32))
+        while c < self.n_pages:
+            c = min(self.n_pages, c + int(step))
+            bounds.append(c)
+            step = min(float(self.ppc), step * self.ramp)
+        n_chunks = len(bounds) - 1
+        cand_s = torch.empty((nq, n_chunks, k), dtype=torch.float32, device=dev)
+        cand_i = torch.empty((nq, n_chunks, k), dtype=torch.int64, device=dev)
+        tmp_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        tmp_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        lib = _lib.load()
+        h = _lib.handle(dev)
+        cs.wait_stream(main)
+        for i in range(n_chunks):
+            b = i & 1
+            c0, c1 = bounds[i], bounds[i + 1]
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(self._consumed[b])
+                self._stage[b][: c1 - c0].copy_(self.host[c0:c1], non_blocking=True)
+                self._loaded[b].record(cs)
+            main.wait_event(self._loaded[b])
+            n = c1 - c0
+            _lib.check(lib.evdr_sharded_search(h, Qb.data_ptr(), qm32.data_ptr(), nq, self._stage[b].data_ptr(),
+                                               n * self.L, self._chunk_off.data_ptr(), n, n * (self.L // CHUNK), k,
+                                               self.page_offset + c0, 0, tmp_s.data_ptr(), tmp_i.data_ptr(),
+                                               _lib.stream_ptr(dev)), "evdr_sharded_search")
+            cand_s[:, i].copy_(tmp_s)
+            cand_i[:, i].copy_(tmp_i)
+            self._consumed[b].record(main)
+        return topk_merge(cand_s.view(nq, n_chunks * k), cand_i.view(nq, n_chunks * k), k)

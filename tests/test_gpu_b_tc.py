@@ -199,6 +199,19 @@ def test_search_api(evdr, cuda):
     assert (s[:, :-1] >= s[:, 1:]).all()
 
 
+@pytest.mark.parametrize("nq,ppc", [(1, 700), (3, 64), (21, 333)])
+def test_host_corpus_search_equals_resident_search(evdr, cuda, nq, ppc):
+    """Top-k over a corpus streamed from pinned host memory (no (nq, np) score matrix) = top-k of the resident scores."""
+    toks = evdr.synth.make_uniform_corpus(2000, 208, device=cuda, seed=12)
+    toks[1500:1504] = toks[3:7]                                   # score ties across chunks: page id decides
+    pm = torch.ones(2000, 208, dtype=torch.bool, device=cuda)
+    Q, qm, _ = evdr.synth.make_queries(toks, pm, nq, 32, seed=13, sigma=2.0, min_len=8, drop=0.1)
+    hc = evdr.HostCorpus(toks.cpu().pin_memory(), cuda, pages_per_chunk=ppc, page_offset=1000)
+    want_s, want_i = evdr.top_k(evdr.PackedPages.from_uniform_tokens(toks).score(Q, qm), 10, id_offset=1000)
+    got_s, got_i = hc.search(Q, qm, 10)
+    assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+
+
 @pytest.mark.parametrize("lq", [33, 50, 64, 100, 128])
 def test_long_queries_split_into_groups(evdr, cuda, lq):
     """Queries of up to 128 tokens stay on the tensor-core path as 32-token groups (exact split)."""
