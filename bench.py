@@ -371,6 +371,7 @@ def main():
         sampler.start()
     ms_step = timed(step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    kernel_flavour = evdr._lib.last_kernel()                          # what the dispatch launched (evdr_last_kernel)
     pairs_per_step = nq * npg * n_gpus
     value = pairs_per_step / (ms_step * 1e-3)
     # the dominant kernel's share of those very steps (CUDA events on its launch stream, warm-up excluded)
@@ -417,7 +418,7 @@ def main():
     # denominator: the measured BURST cuBLAS bf16 peak (the higher of the two measured figures, so the
     # fraction can only be understated); each launch runs ~0.57 s at the power cap, where cuBLAS itself
     # sustains bf16_tflops_sustained -- reported beside it
-    roofline = {"kernel": "maxsim_tc_kernel<2,256,3,CG2,...,EW=8> (cta_group::2 pairs, two epilogue groups)",
+    roofline = {"kernel": kernel_flavour,
                 "bound": "tensor", "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"],

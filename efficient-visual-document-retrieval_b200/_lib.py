@@ -35,6 +35,7 @@ _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 _SIGNATURES = {
     "evdr_version": ([], _i),
     "evdr_last_error": ([], C.c_char_p),
+    "evdr_last_kernel": ([], C.c_char_p),
     "evdr_create": ([_i, C.POINTER(_vp)], _i),
     "evdr_destroy": ([_vp], _i),
     "evdr_sm_count": ([_vp], _i),
@@ -111,6 +112,12 @@ def load() -> C.CDLL:
 
 def last_error() -> str:
     msg = load().evdr_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def last_kernel() -> str:
+    """Name + template arguments of the scoring kernel this thread launched last (evdr_last_kernel)."""
+    msg = load().evdr_last_kernel()
     return msg.decode("utf-8", "replace") if msg else ""
 
 

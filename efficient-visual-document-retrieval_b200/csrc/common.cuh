@@ -24,6 +24,10 @@ namespace evdr {
 
 char* tls_error_buf();
 int set_error(int code, const char* fmt, ...);
+// name + template arguments of the scoring kernel this thread launched last (evdr_last_kernel): lets tests and
+// benchmarks assert WHICH flavour the dispatch picked
+char* tls_kernel_buf();
+void note_kernel(const char* fmt, ...);
 
 #define EVDR_CHECK_ARG(cond, ...)                                        \
   do {                                                                   \

@@ -16,11 +16,25 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+char* tls_kernel_buf() {
+  static thread_local char buf[160] = {0};
+  return buf;
+}
+
+void note_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tls_kernel_buf(), 160, fmt, ap);
+  va_end(ap);
+}
+
 }  // namespace evdr
 
 extern "C" {
 
 int evdr_version(void) { return EVDR_VERSION_INT; }
+
+const char* evdr_last_kernel(void) { return evdr::tls_kernel_buf(); }
 
 const char* evdr_last_error(void) { return evdr::tls_error_buf(); }
 

@@ -340,6 +340,7 @@ static int launch_scan(evdr_handle* h, const void* Qb, const void* tokens, int64
     return set_error(EVDR_ERR_UNSUPPORTED, "scan kernel needs %d B of shared memory", S::TOTAL);
   EVDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   prm.sched = h->sched_ring + (h->sched_next.fetch_add(1, std::memory_order_relaxed) % EVDR_SCHED_RING);
+  note_kernel("maxsim_scan_kernel<NQ=%d> grid=%d topk=%d", NQ, grid, prm.tk_k);
   kern<<<grid, 192, S::TOTAL, st>>>(tmQ, tmP, prm);
   EVDR_LAUNCH_CHECK("maxsim_scan_kernel");
   return EVDR_OK;

@@ -731,6 +731,8 @@ static int launch_tc(evdr_handle* h, const void* Qb, const void* tokens, int64_t
     // kernel hands its slot back zeroed (the CTA that draws the last terminal value resets it)
     prm.sched = h->sched_ring + (h->sched_next.fetch_add(1, std::memory_order_relaxed) % EVDR_SCHED_RING);
   }
+  note_kernel("maxsim_tc_kernel<R=%d,BN=%d,STAGES=%d,CG2=%d,AM=%d,KB=%d,SP=%d,EW=%d,TA=%d,TK=%d> grid=%u", R, BN, STAGES,
+              (int)CG2, (int)AM, KB, (int)SP, EW, (int)TA, (int)TK, cfg.gridDim.x);
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmQ, tmP, prm);
   if (le != cudaSuccess)
     return set_error(EVDR_ERR_CUDA, "launch of maxsim_tc_kernel failed: %s", cudaGetErrorString(le));

@@ -61,6 +61,9 @@ enum evdr_dtype { EVDR_F32 = 0, EVDR_BF16 = 1 };
 
 EVDR_API int evdr_version(void);
 EVDR_API const char* evdr_last_error(void);
+/* Name and template arguments of the MaxSim scoring kernel the calling thread launched last (thread-local, ""
+ * before the first launch): which flavour the dispatch picked, for tests, benchmarks and bug reports. */
+EVDR_API const char* evdr_last_kernel(void);
 
 /* Handle: per (thread, device); holds the device ordinal, SM count, the driver
  * entry point used to encode TMA descriptors and, after evdr_comm_init, the NCCL

@@ -54,6 +54,10 @@ def test_A1_bench_flavour_two_epilogue_groups_on_1040_slot_pages(evdr, cuda, nq,
     pk = evdr.PackedPages.from_uniform_tokens(toks)
     Qb, qm32 = evdr.pack_queries(Q, qm)
     got = pk.score_packed(Qb, qm32)
+    flavour = evdr._lib.last_kernel()
+    want = {None: "CG2=1,AM=0,KB=1,SP=0,EW=8" if nq % 16 == 0 else "CG2=0,AM=0,KB=1,SP=0,EW=8",      # 100 queries = 25 tiles
+            "pair": "CG2=1,AM=0,KB=1,SP=0,EW=4", "1cta": "CG2=0,AM=0,KB=1,SP=0,EW=4"}[mode]
+    assert want in flavour, flavour                              # the default IS the flavour bench.py times
     qs, cs = slice(3, 19), slice(101, 165)
     want = mo.maxsim_masked(Q[qs].float().cpu().numpy(), toks[cs].float().cpu().numpy(), qm[qs].cpu().numpy(),
                             pm[cs].cpu().numpy())
@@ -304,3 +308,31 @@ def test_e_sharded_merge_on_one_rank_equals_global_topk(evdr, cuda):
     mv, mi = evdr.topk_merge(torch.cat([v0, v1], 1), torch.cat([i0, i1], 1), 10)
     gv, gi = evdr.top_k(s, 10)
     assert torch.equal(mi, gi) and torch.equal(mv, gv)
+
+
+def test_dispatch_picks_the_documented_flavour(evdr, cuda, monkeypatch):
+    """which kernel runs for which shape (evdr_last_kernel)."""
+    monkeypatch.delenv("EVDR_TC_MODE", raising=False)
+    long_pages = evdr.PackedPages.from_uniform_tokens(evdr.synth.make_uniform_corpus(400, 1040, device=cuda, seed=3))
+    short_pages = evdr.PackedPages.from_uniform_tokens(evdr.synth.make_uniform_corpus(4000, 64, device=cuda, seed=4))
+
+    def flavour(pk, nq, search=False, k_blocks=1):
+        Q = torch.nn.functional.normalize(torch.randn(nq, 32, 128, device=cuda), dim=-1)
+        qm = torch.ones(nq, 32, dtype=torch.bool, device=cuda)
+        pk.search(Q, qm, 10) if search else pk.score(Q, qm)
+        return evdr._lib.last_kernel()
+
+    assert "maxsim_scan_kernel<NQ=1>" in flavour(long_pages, 1)
+    assert "maxsim_scan_kernel<NQ=2>" in flavour(long_pages, 2) and "topk=10" in flavour(long_pages, 2, search=True)
+    assert "R=1,BN=256,STAGES=3,CG2=0" in flavour(long_pages, 4) and "TK=1" in flavour(long_pages, 4, search=True)
+    assert "TA=1" in flavour(long_pages, 8) and "TA=1,TK=1" in flavour(long_pages, 8, search=True)
+    assert "R=3,BN=256,STAGES=2,CG2=0" in flavour(long_pages, 12)
+    assert "R=2,BN=256,STAGES=3,CG2=1" in flavour(long_pages, 16) and "EW=8" in flavour(long_pages, 16)
+    assert "R=3,BN=256,STAGES=4,CG2=1" in flavour(long_pages, 24)              # six tiles: one pair group
+    assert "CG2=0" in flavour(long_pages, 100)                                   # 25 tiles would idle 3 of 28 slots
+    assert "CG2=1" in flavour(long_pages, 1024) and "TK=0" in flavour(long_pages, 1024, search=True)
+    assert "SP=1,EW=4" in flavour(short_pages, 1) and "SP=1,EW=4,TA=0,TK=1" in flavour(short_pages, 3, search=True)
+    assert "CG2=0" in flavour(short_pages, 8) and "SP=1,EW=8" in flavour(short_pages, 8)
+    assert "CG2=1" in flavour(short_pages, 64) and "SP=1,EW=8" in flavour(short_pages, 64)
+    x3 = evdr.PackedPages.from_padded(torch.randn(300, 200, 128, device=cuda), torch.ones(300, 200, dtype=torch.bool, device=cuda), k_blocks=3)
+    assert "CG2=1,AM=0,KB=3" in flavour(x3, 32) and "BN=128,STAGES=2,CG2=0,AM=0,KB=3" in flavour(x3, 3)
